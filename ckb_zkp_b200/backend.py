@@ -1,0 +1,268 @@
+"""Thin object layer over the C ABI: one `Context` per GPU, numpy arrays in and out.
+
+Array conventions (identical to the bytes ark-ff 0.2 keeps in memory, see include/zkb.h):
+  Fr vector      uint64[n, 4]                      Montgomery unless a function says canonical
+  G1 points      uint64[n, 2 * L]  (x || y)        L = 4 (BN254) or 6 (BLS12-381), Montgomery
+  G2 points      uint64[n, 4 * L]  (x.c0 || x.c1 || y.c0 || y.c1)
+  infinity       uint8[n]                          1 = identity (coordinates ignored)
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import BLS12_381, BN254, G1, G2, Csr
+
+FQ_LIMBS = {BN254: 4, BLS12_381: 6}
+
+
+def point_words(curve, group):
+    """u64 words of one affine point."""
+    return FQ_LIMBS[curve] * 2 * (2 if group == G2 else 1)
+
+
+class ZkbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("zkb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _fr(a, what="scalars"):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError("%s must be uint64[n, 4]" % what)
+    return a
+
+
+class CsrMatrix:
+    """Row-major sparse matrix = flattened ProvingAssignment::{at,bt,ct} (groth16/src/prover.rs:16-25)."""
+
+    def __init__(self, row_ptr, col_idx, coeff_mont):
+        self.row_ptr = np.ascontiguousarray(row_ptr, dtype=np.uint32)
+        self.col_idx = np.ascontiguousarray(col_idx, dtype=np.uint32)
+        self.coeff = np.ascontiguousarray(coeff_mont, dtype=np.uint64).reshape(-1, 4)
+        if len(self.row_ptr) == 0:
+            raise ValueError("row_ptr needs n_rows + 1 entries")
+        if len(self.col_idx) != len(self.coeff) or int(self.row_ptr[-1]) != len(self.col_idx):
+            raise ValueError("inconsistent CSR arrays")
+        self.c = Csr(len(self.row_ptr) - 1, len(self.col_idx), self.row_ptr.ctypes.data, self.col_idx.ctypes.data,
+                     self.coeff.ctypes.data)
+
+    @property
+    def n_rows(self):
+        return len(self.row_ptr) - 1
+
+    @property
+    def nnz(self):
+        return len(self.col_idx)
+
+
+class Srs:
+    """Bases resident in HBM (the `&[G::Affine]` of VariableBaseMSM::multi_scalar_mul)."""
+
+    def __init__(self, ctx, handle, curve, group, n):
+        self.ctx, self.handle, self.curve, self.group, self.n = ctx, handle, curve, group, n
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zkb_srs_free(self.handle)
+            self.handle = None
+
+    def __len__(self):
+        return self.n
+
+
+class ProvingKey:
+    """groth16 Parameters<E> (groth16/src/lib.rs:81-91) resident in HBM."""
+
+    def __init__(self, ctx, handle, curve):
+        self.ctx, self.handle, self.curve = ctx, handle, curve
+
+    def free(self):
+        if self.handle:
+            self.ctx.lib.zkb_groth16_pk_free(self.handle)
+            self.handle = None
+
+
+class Context:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        rc = self.lib.zkb_init(device, ctypes.byref(h))
+        if rc != 0:
+            raise ZkbError(rc, "zkb_init(device=%d) failed: no usable B200 (sm_100) device -- this backend has no "
+                               "CPU fallback" % device)
+        self.handle = h
+        self.device = device
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise ZkbError(rc, self.lib.zkb_last_error(self.handle).decode())
+
+    def close(self):
+        if self.handle:
+            self.lib.zkb_destroy(self.handle)
+            self.handle = None
+
+    def sync(self):
+        self._check(self.lib.zkb_sync(self.handle))
+
+    @property
+    def stream(self):
+        return self.lib.zkb_stream(self.handle)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.zkb_launch_count(self.handle))
+
+    # -- SRS / MSM ----------------------------------------------------------------------------
+    def srs_upload(self, curve, group, xy, inf=None, precompute=True):
+        xy = np.ascontiguousarray(xy, dtype=np.uint64)
+        w = point_words(curve, group)
+        if xy.ndim != 2 or xy.shape[1] != w:
+            raise ValueError("bases must be uint64[n, %d]" % w)
+        n = xy.shape[0]
+        inf = np.zeros(n, dtype=np.uint8) if inf is None else np.ascontiguousarray(inf, dtype=np.uint8)
+        if inf.shape != (n,):
+            raise ValueError("infinity flags must be uint8[n]")
+        h = ctypes.c_void_p()
+        self._check(self.lib.zkb_srs_upload(self.handle, curve, group, _ptr(xy), _ptr(inf), n,
+                                            _lib.SRS_PRECOMPUTE if precompute else 0, ctypes.byref(h)))
+        return Srs(self, h, curve, group, n)
+
+    def msm(self, srs, scalars, base_offset=0, mont=False):
+        """sum scalars[i] * bases[base_offset + i]; returns (xy uint64[words], is_identity)."""
+        scalars = _fr(scalars)
+        out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        fn = self.lib.zkb_msm_mont if mont else self.lib.zkb_msm
+        self._check(fn(self.handle, srs.handle, base_offset, _ptr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
+    def msm_dev(self, srs, d_scalars_ptr, n, base_offset=0):
+        """Same with canonical scalars already in device memory (raw device pointer)."""
+        out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_dev(self.handle, srs.handle, base_offset, ctypes.c_void_p(d_scalars_ptr), n,
+                                         _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
+    def fixed_base_mul(self, curve, group, base_xy, scalars):
+        scalars = _fr(scalars)
+        base_xy = np.ascontiguousarray(base_xy, dtype=np.uint64).reshape(-1)
+        w = point_words(curve, group)
+        if base_xy.shape[0] != w:
+            raise ValueError("base must be uint64[%d]" % w)
+        n = scalars.shape[0]
+        out = np.zeros((n, w), dtype=np.uint64)
+        oinf = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.zkb_fixed_base_mul(self.handle, curve, group, _ptr(base_xy), _ptr(scalars), n, _ptr(out),
+                                                _ptr(oinf)))
+        return out, oinf
+
+    # -- NTT ----------------------------------------------------------------------------------
+    def ntt(self, curve, data, log_n, inverse=False, coset=False):
+        """In-place transform of uint64[2^log_n, 4] (Montgomery), natural order in and out."""
+        if not (isinstance(data, np.ndarray) and data.dtype == np.uint64 and data.flags.c_contiguous
+                and data.shape == (1 << log_n, 4)):
+            raise ValueError("data must be a contiguous uint64[2^log_n, 4] array")
+        flags = (_lib.NTT_INVERSE if inverse else 0) | (_lib.NTT_COSET if coset else 0)
+        self._check(self.lib.zkb_ntt(self.handle, curve, _ptr(data), log_n, flags))
+        return data
+
+    def ntt_dev(self, curve, d_ptr, log_n, inverse=False, coset=False):
+        flags = (_lib.NTT_INVERSE if inverse else 0) | (_lib.NTT_COSET if coset else 0)
+        self._check(self.lib.zkb_ntt_dev(self.handle, curve, ctypes.c_void_p(d_ptr), log_n, flags))
+
+    def fr_convert(self, curve, a, to_mont):
+        a = _fr(a, "elements")
+        out = np.empty_like(a)
+        self._check(self.lib.zkb_fr_convert(self.handle, curve, _ptr(a), _ptr(out), a.shape[0], 1 if to_mont else 0))
+        return out
+
+    # -- Groth16 ------------------------------------------------------------------------------
+    def groth16_h(self, curve, A, B, C, z_mont, n_inputs, n_aux):
+        z = _fr(z_mont, "assignment")
+        if z.shape[0] != n_inputs + n_aux:
+            raise ValueError("assignment length != n_inputs + n_aux")
+        need = A.n_rows + n_inputs
+        log_n = max(need - 1, 0).bit_length()
+        h = np.zeros((1 << log_n, 4), dtype=np.uint64)
+        self._check(self.lib.zkb_groth16_h(self.handle, curve, ctypes.byref(A.c), ctypes.byref(B.c), ctypes.byref(C.c),
+                                           _ptr(z), n_inputs, n_aux, _ptr(h)))
+        return h
+
+    def groth16_pk(self, curve, a, b_g1, b_g2, h, l, g1_singles, g2_singles):
+        """a, b_g1, b_g2, h, l: (xy, inf) pairs; g1_singles = [alpha, beta, delta], g2_singles = [beta, delta]."""
+        args = []
+        for (xy, inf), group in ((a, G1), (b_g1, G1), (b_g2, G2), (h, G1), (l, G1)):
+            xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, point_words(curve, group))
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+            if inf.shape != (xy.shape[0],):
+                raise ValueError("infinity flags / points mismatch")
+            args.append((xy, inf))
+        s1 = np.ascontiguousarray(g1_singles, dtype=np.uint64).reshape(3, point_words(curve, G1))
+        s2 = np.ascontiguousarray(g2_singles, dtype=np.uint64).reshape(2, point_words(curve, G2))
+        flat = []
+        for xy, inf in args:
+            flat += [_ptr(xy), _ptr(inf), xy.shape[0]]
+        hdl = ctypes.c_void_p()
+        self._check(self.lib.zkb_groth16_pk_create(self.handle, curve, *flat, _ptr(s1), _ptr(s2), ctypes.byref(hdl)))
+        return ProvingKey(self, hdl, curve)
+
+    def _proof_arrays(self, curve):
+        w1, w2 = point_words(curve, G1), point_words(curve, G2)
+        return np.zeros(2 * w1 + w2, dtype=np.uint64), np.zeros(3, dtype=np.uint8), w1, w2
+
+    @staticmethod
+    def _split_proof(buf, inf, w1, w2):
+        return (buf[:w1].copy(), bool(inf[0])), (buf[w1:w1 + w2].copy(), bool(inf[1])), (buf[w1 + w2:].copy(), bool(inf[2]))
+
+    def groth16_prove(self, pk, A, B, C, z_mont, n_inputs, n_aux, r, s):
+        """zkb_groth16_prove: host buffers in, proof (A, B, C) out as ((xy, is_identity), ...)."""
+        z = _fr(z_mont, "assignment")
+        if z.shape[0] != n_inputs + n_aux:
+            raise ValueError("assignment length != n_inputs + n_aux")
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        buf, inf, w1, w2 = self._proof_arrays(pk.curve)
+        self._check(self.lib.zkb_groth16_prove(self.handle, pk.handle, ctypes.byref(A.c), ctypes.byref(B.c),
+                                               ctypes.byref(C.c), _ptr(z), n_inputs, n_aux, _ptr(r), _ptr(s), _ptr(buf),
+                                               _ptr(inf)))
+        return self._split_proof(buf, inf, w1, w2)
+
+    def groth16_stage(self, pk, A, B, C, z_mont, n_inputs, n_aux):
+        z = _fr(z_mont, "assignment")
+        self._check(self.lib.zkb_groth16_stage(self.handle, pk.handle, ctypes.byref(A.c), ctypes.byref(B.c),
+                                               ctypes.byref(C.c), _ptr(z), n_inputs, n_aux))
+
+    def groth16_prove_staged(self, pk, r, s):
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        self._check(self.lib.zkb_groth16_prove_staged(self.handle, pk.handle, _ptr(r), _ptr(s)))
+
+    def groth16_fetch_proof(self, pk):
+        buf, inf, w1, w2 = self._proof_arrays(pk.curve)
+        self._check(self.lib.zkb_groth16_fetch_proof(self.handle, pk.handle, _ptr(buf), _ptr(inf)))
+        return self._split_proof(buf, inf, w1, w2)
+
+    # -- diagnostics --------------------------------------------------------------------------
+    def debug_fp_op(self, field, op, a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint32)
+        b = np.ascontiguousarray(b, dtype=np.uint32)
+        out = np.zeros_like(a)
+        self._check(self.lib.zkb_debug_fp_op(self.handle, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
+    def debug_pt_op(self, curve, group, op, acc, q, neg, out_words):
+        acc = np.ascontiguousarray(acc, dtype=np.uint32)
+        q = None if q is None else np.ascontiguousarray(q, dtype=np.uint32)
+        out = np.zeros((acc.shape[0], out_words), dtype=np.uint32)
+        self._check(self.lib.zkb_debug_pt_op(self.handle, curve, group, op, _ptr(acc), _ptr(q), 1 if neg else 0,
+                                             _ptr(out), acc.shape[0]))
+        return out

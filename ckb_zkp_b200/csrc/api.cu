@@ -1,0 +1,266 @@
+// C-ABI entry points of libzkb (include/zkb.h): context, SRS residency, MSM, NTT, Fr helpers.
+// The Groth16 entry points live in groth16_api.cu.  Device code only -- there is no CPU
+// fallback: without a usable CUDA device zkb_init fails with ZKB_E_NO_DEVICE.
+#include <cstring>
+
+#include "common.cuh"
+#include "groth16.cuh"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace zkb {
+
+const GroupOps* group_ops_bn_g1();
+const GroupOps* group_ops_bn_g2();
+const GroupOps* group_ops_bls_g1();
+const GroupOps* group_ops_bls_g2();
+
+const GroupOps* group_ops(int curve, int group) {
+  if (curve == ZKB_BN254) return group == ZKB_G1 ? group_ops_bn_g1() : group == ZKB_G2 ? group_ops_bn_g2() : nullptr;
+  if (curve == ZKB_BLS12_381) return group == ZKB_G1 ? group_ops_bls_g1() : group == ZKB_G2 ? group_ops_bls_g2() : nullptr;
+  return nullptr;
+}
+
+// out[i] = into_repr(in[i]) (mode 0) / from_repr(in[i]) (mode 1)
+template <class FrP>
+__global__ void k_fr_convert(const Fp<FrP>* in, Fp<FrP>* out, size_t n, int mode) {   // in may alias out
+  using Fr = Fp<FrP>;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr v = ld_vec_rw(&in[i]);
+    v = mode == 0 ? Fr::from_mont(v) : Fr::to_mont(v);
+    st_vec(&out[i], v);
+  }
+}
+
+int fr_convert_dev(zkb_ctx* ctx, cudaStream_t st, int curve, const void* d_in, void* d_out, size_t n, int mode) {
+  if (n == 0) return ZKB_OK;
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > (unsigned)ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+  if (curve == ZKB_BLS12_381)
+    ZKB_LAUNCH(ctx, (k_fr_convert<BlsFr>), blocks, 256, 0, st, (const Fp<BlsFr>*)d_in, (Fp<BlsFr>*)d_out, n, mode);
+  else
+    ZKB_LAUNCH(ctx, (k_fr_convert<BnFr>), blocks, 256, 0, st, (const Fp<BnFr>*)d_in, (Fp<BnFr>*)d_out, n, mode);
+  return ZKB_OK;
+}
+
+static bool valid_curve(int curve) { return curve == ZKB_BN254 || curve == ZKB_BLS12_381; }
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+int zkb_init(int device, zkb_ctx** out) {
+  if (!out) return ZKB_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return ZKB_E_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return ZKB_E_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return ZKB_E_NO_DEVICE;
+  if (prop.major != 10) return ZKB_E_NO_DEVICE;   // sm_100a cubins only
+  zkb_ctx* ctx = new zkb_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  bool ok = cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < kNumSideStreams; i++) {
+    ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  ctx->pinned_bytes = 1 << 16;
+  ok = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;
+  if (ok) {
+    // keep freed scratch cached in the pool: the prove path allocates the same sizes every proof
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
+  if (!ok) {
+    zkb_destroy(ctx);
+    return ZKB_E_CUDA;
+  }
+  *out = ctx;
+  return ZKB_OK;
+}
+
+void zkb_destroy(zkb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  groth16_free_stage(ctx);
+  ntt_free_domains(ctx);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int i = 0; i < kNumSideStreams; i++) {
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->main) cudaStreamDestroy(ctx->main);
+  delete ctx;
+}
+
+const char* zkb_last_error(zkb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* zkb_stream(zkb_ctx* ctx) { return ctx ? (void*)ctx->main : nullptr; }
+uint64_t zkb_launch_count(zkb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zkb_sync(zkb_ctx* ctx) {
+  if (!ctx) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+  return ZKB_OK;
+}
+
+// ---- SRS -----------------------------------------------------------------------------------
+int zkb_srs_upload(zkb_ctx* ctx, int curve, int group, const uint64_t* xy_mont, const uint8_t* inf, size_t n,
+                   unsigned flags, zkb_srs** out) {
+  if (!ctx || !out) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = nullptr;
+  const GroupOps* ops = group_ops(curve, group);
+  if (!ops) return set_err(ctx, ZKB_E_INVALID, "srs_upload: unknown curve %d / group %d", curve, group);
+  if (n && (!xy_mont || !inf)) return set_err(ctx, ZKB_E_INVALID, "srs_upload: null bases");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  zkb_srs* srs = new zkb_srs();
+  srs->ctx = ctx; srs->curve = curve; srs->group = group; srs->n = n;
+  srs->table = nullptr; srs->inf = nullptr;
+  int rc = ops->srs_build(ctx, srs, xy_mont, inf, flags);
+  if (rc != ZKB_OK) {
+    zkb_srs_free(srs);
+    return rc;
+  }
+  *out = srs;
+  return ZKB_OK;
+}
+
+void zkb_srs_free(zkb_srs* srs) {
+  if (!srs) return;
+  cudaSetDevice(srs->ctx->device);
+  if (srs->table) cudaFree(srs->table);
+  if (srs->inf) cudaFree(srs->inf);
+  delete srs;
+}
+
+size_t zkb_srs_len(const zkb_srs* srs) { return srs ? srs->n : 0; }
+
+// ---- MSM -----------------------------------------------------------------------------------
+static int msm_host(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+                    int mont, uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !srs || !out_xy || !out_inf || (n && !scalars)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm: srs belongs to another context");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  // ark's multi_scalar_mul zips bases and scalars: the shorter one wins (groth16/src/prover.rs:187)
+  size_t avail = base_offset <= srs->n ? srs->n - base_offset : 0;
+  if (n > avail) n = avail;
+  const GroupOps* ops = group_ops(srs->curve, srs->group);
+  Scratch ws(ctx, ctx->main);
+  uint32_t* d_scalars;
+  ZKB_TRY(ws.alloc(&d_scalars, n * 8));
+  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, ctx->main));
+  return ops->msm_to_host(ctx, srs, base_offset, d_scalars, n, mont, out_xy, out_inf);
+}
+
+int zkb_msm(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars_canonical, size_t n,
+            uint64_t* out_xy, uint8_t* out_inf) {
+  return msm_host(ctx, srs, base_offset, scalars_canonical, n, 0, out_xy, out_inf);
+}
+int zkb_msm_mont(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars_mont, size_t n,
+                 uint64_t* out_xy, uint8_t* out_inf) {
+  return msm_host(ctx, srs, base_offset, scalars_mont, n, 1, out_xy, out_inf);
+}
+int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void* d_scalars_canonical, size_t n,
+                uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !srs || !out_xy || !out_inf || (n && !d_scalars_canonical)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm: srs belongs to another context");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t avail = base_offset <= srs->n ? srs->n - base_offset : 0;
+  if (n > avail) n = avail;
+  return group_ops(srs->curve, srs->group)
+      ->msm_to_host(ctx, srs, base_offset, (const uint32_t*)d_scalars_canonical, n, 0, out_xy, out_inf);
+}
+
+// ---- NTT -----------------------------------------------------------------------------------
+int zkb_ntt_dev(zkb_ctx* ctx, int curve, void* d_data_mont, unsigned log_n, unsigned flags) {
+  if (!ctx || !d_data_mont) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!valid_curve(curve)) return set_err(ctx, ZKB_E_INVALID, "ntt: unknown curve %d", curve);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NttDomain* dom;
+  ZKB_TRY(ntt_get_domain(ctx, curve, log_n, &dom));
+  Scratch ws(ctx, ctx->main);
+  uint32_t* scratch;
+  ZKB_TRY(ws.alloc(&scratch, dom->n * 8));
+  return ntt_run(ctx, ctx->main, dom, d_data_mont, scratch, flags);
+}
+
+int zkb_ntt(zkb_ctx* ctx, int curve, uint64_t* data_mont, unsigned log_n, unsigned flags) {
+  if (!ctx || !data_mont) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!valid_curve(curve)) return set_err(ctx, ZKB_E_INVALID, "ntt: unknown curve %d", curve);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  NttDomain* dom;
+  ZKB_TRY(ntt_get_domain(ctx, curve, log_n, &dom));
+  Scratch ws(ctx, ctx->main);
+  uint32_t *data, *scratch;
+  ZKB_TRY(ws.alloc(&data, dom->n * 8));
+  ZKB_TRY(ws.alloc(&scratch, dom->n * 8));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(data, data_mont, dom->n * 32, cudaMemcpyHostToDevice, ctx->main));
+  ZKB_TRY(ntt_run(ctx, ctx->main, dom, data, scratch, flags));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(data_mont, data, dom->n * 32, cudaMemcpyDeviceToHost, ctx->main));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+  return ZKB_OK;
+}
+
+// ---- fixed-base multiplication ---------------------------------------------------------------
+int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_xy_mont,
+                       const uint64_t* scalars_canonical, size_t n, uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !base_xy_mont || (n && (!scalars_canonical || !out_xy || !out_inf))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const GroupOps* ops = group_ops(curve, group);
+  if (!ops) return set_err(ctx, ZKB_E_INVALID, "fixed_base_mul: unknown curve %d / group %d", curve, group);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint8_t *d_base, *d_out, *d_inf;
+  uint32_t* d_sc;
+  ZKB_TRY(ws.alloc(&d_base, ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_sc, n * 8));
+  ZKB_TRY(ws.alloc(&d_out, n * ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_inf, n));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_base, base_xy_mont, ops->affine_bytes, cudaMemcpyHostToDevice, st));
+  if (n) {
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_sc, scalars_canonical, n * 32, cudaMemcpyHostToDevice, st));
+    ZKB_TRY(ops->fixed_base_mul(ctx, st, d_base, d_sc, n, d_out, d_inf));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy, d_out, n * ops->affine_bytes, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, n, cudaMemcpyDeviceToHost, st));
+  }
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+// ---- Fr helpers ------------------------------------------------------------------------------
+int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode) {
+  if (!ctx || (n && (!in || !out)) || (mode != 0 && mode != 1)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!valid_curve(curve)) return set_err(ctx, ZKB_E_INVALID, "fr_convert: unknown curve %d", curve);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint32_t* d;
+  ZKB_TRY(ws.alloc(&d, n * 8));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d, in, n * 32, cudaMemcpyHostToDevice, st));
+  ZKB_TRY(fr_convert_dev(ctx, st, curve, d, d, n, mode));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d, n * 32, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+}  // extern "C"

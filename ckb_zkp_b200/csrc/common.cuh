@@ -1,0 +1,124 @@
+// Shared host-side plumbing of the C-ABI library: context, streams, error capture,
+// stream-ordered workspace allocation, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/zkb.h"
+
+namespace zkb {
+
+constexpr int kNumSideStreams = 6;
+constexpr int kSMs = 148;   // B200
+
+struct NttDomain;           // ntt.cu
+struct Groth16Stage;        // groth16.cu
+
+}  // namespace zkb
+
+struct zkb_ctx {
+  int device = 0;
+  cudaStream_t main = nullptr;
+  cudaStream_t side[zkb::kNumSideStreams] = {};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[zkb::kNumSideStreams] = {};
+  std::mutex mu;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = zkb::kSMs;
+  std::map<int, zkb::NttDomain*> domains;   // key = curve * 64 + log_n
+  zkb::Groth16Stage* stage = nullptr;
+  // pinned bounce buffer for small results
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+namespace zkb {
+
+inline int set_err(zkb_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+#define ZKB_CUDA(ctx, expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return zkb::set_err(ctx, ZKB_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                          cudaGetErrorString(e__));                                           \
+  } while (0)
+
+#define ZKB_TRY(expr)            \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != ZKB_OK) return rc__; \
+  } while (0)
+
+// kernel launch with accounting + error check
+#define ZKB_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                               \
+  do {                                                                                        \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                               \
+    (ctx)->launches++;                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess)                                                                   \
+      return zkb::set_err(ctx, ZKB_E_CUDA, "launch %s failed at %s:%d: %s", #kernel, __FILE__, \
+                          __LINE__, cudaGetErrorString(e__));                                 \
+  } while (0)
+
+// stream-ordered scratch allocation (the default mempool keeps freed blocks cached)
+struct Scratch {
+  zkb_ctx* ctx;
+  cudaStream_t stream;
+  std::vector<void*> ptrs;
+  Scratch(zkb_ctx* c, cudaStream_t s) : ctx(c), stream(s) {}
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, stream);
+  }
+  template <class T>
+  int alloc(T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+    if (e != cudaSuccess)
+      return set_err(ctx, ZKB_E_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    ptrs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return ZKB_OK;
+  }
+};
+
+inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+inline unsigned ceil_log2(size_t n) {
+  unsigned l = 0;
+  while ((size_t(1) << l) < n) l++;
+  return l;
+}
+
+// fork side streams from main / join them back
+inline int fork_streams(zkb_ctx* ctx, int n) {
+  ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->main));
+  for (int i = 0; i < n; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+  return ZKB_OK;
+}
+inline int join_streams(zkb_ctx* ctx, int n) {
+  for (int i = 0; i < n; i++) {
+    ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+    ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->main, ctx->ev_join[i], 0));
+  }
+  return ZKB_OK;
+}
+
+}  // namespace zkb

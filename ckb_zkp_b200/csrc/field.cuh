@@ -1,0 +1,244 @@
+// Prime-field arithmetic in Montgomery form on 32-bit limbs (R = 2^(32*N)), and the
+// quadratic extension Fq2 = Fq[u]/(u^2 + 1) used by both G2 groups.
+//
+// Replaces what the reference obtains from ark-ff 0.2 `Fp256/Fp384` (Montgomery,
+// R = 2^(64*limbs): identical R, identical bytes in memory -- u64 LE limbs are two
+// u32 LE limbs), i.e. the arithmetic underneath groth16/src/prover.rs:187-228 and
+// groth16/src/r1cs_to_qap.rs:131-169.
+//
+// Multiplication is a word-serial CIOS: for every limb b[i] the products a[j]*b[i]
+// are added in two carry chains (even j / odd j) of mad.lo.cc + madc.hi.cc pairs,
+// which ptxas fuses into IMAD.WIDE.U32 with carry; then one Montgomery step
+// (m = T[0] * -p^-1, T += m*p, shift one limb).  All values stay fully reduced
+// (< p) so equality tests are plain limb compares.
+#pragma once
+#include "field_params.cuh"
+
+namespace zkb {
+
+template <class P>
+struct alignas(16) Fp {
+  static constexpr int N = P::N;
+  using Params = P;
+  uint32_t v[N];
+
+  ZKB_HD static Fp zero() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = 0;
+    return r;
+  }
+  ZKB_HD static Fp one() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::one(i);
+    return r;
+  }
+  ZKB_HD static Fp r2() {
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = P::r2(i);
+    return r;
+  }
+  ZKB_HD bool is_zero() const {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) t |= v[i];
+    return t == 0;
+  }
+  ZKB_HD bool operator==(const Fp& o) const {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) t |= v[i] ^ o.v[i];
+    return t == 0;
+  }
+  ZKB_HD bool operator!=(const Fp& o) const { return !(*this == o); }
+
+  // r = a + b mod p
+  ZKB_HD static Fp add(const Fp& a, const Fp& b) {
+    Fp s, t;
+    s.v[0] = ptx::add_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) s.v[i] = ptx::addc_cc(a.v[i], b.v[i]);
+    s.v[N - 1] = ptx::addc(a.v[N - 1], b.v[N - 1]);   // 2p < 2^(32N): no carry out
+    t.v[0] = ptx::sub_cc(s.v[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t.v[i] = ptx::subc_cc(s.v[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);                 // 0xffffffff when s < p
+#pragma unroll
+    for (int i = 0; i < N; i++) s.v[i] = borrow ? s.v[i] : t.v[i];
+    return s;
+  }
+  // r = a - b mod p
+  ZKB_HD static Fp sub(const Fp& a, const Fp& b) {
+    Fp d;
+    d.v[0] = ptx::sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) d.v[i] = ptx::subc_cc(a.v[i], b.v[i]);
+    uint32_t borrow = ptx::subc(0, 0);
+    d.v[0] = ptx::add_cc(d.v[0], P::mod(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) d.v[i] = ptx::addc_cc(d.v[i], P::mod(i) & borrow);
+    d.v[N - 1] = ptx::addc(d.v[N - 1], P::mod(N - 1) & borrow);
+    return d;
+  }
+  ZKB_HD static Fp neg(const Fp& a) { return sub(zero(), a); }
+  ZKB_HD static Fp dbl(const Fp& a) { return add(a, a); }
+
+  // ---- Montgomery multiplication -------------------------------------------------
+  // The running value is kept as T = X + 2^32 * Y in two N-limb accumulators so that
+  // every 64-bit partial product lands on an even-aligned register pair of one of them
+  // (IMAD.WIDE needs aligned pairs; a single array would need a realigning MOV per limb
+  // per row).  Products of even columns a[j] go to X at limbs (j, j+1); products of odd
+  // columns go to Y at limbs (j-1, j).  One row = multiply-accumulate by b_i, then one
+  // Montgomery step m = X[0] * (-p^-1), T += m * p, which zeroes X[0].  Dividing by 2^32
+  // swaps the roles: T/2^32 = Y + X[1] + 2^32 * (X >> 64), i.e. Y becomes the even
+  // accumulator of the next row (plus the straggler X[1], whose carry has exactly the
+  // weight of limb 0 of the new odd accumulator) and X >> 64 the new odd accumulator.
+
+  // Y chain for odd columns: (Y[j-1], Y[j]) += c[j] * s
+  template <class Acc>
+  ZKB_HD static void odd_chain(uint32_t* Y, Acc c, uint32_t s) {
+    ptx::mad_wide_cc(Y[0], Y[1], c(1), s);
+#pragma unroll
+    for (int j = 3; j < N; j += 2) ptx::madc_wide_cc(Y[j - 1], Y[j], c(j), s);
+  }
+  // X chain for even columns: (X[j], X[j+1]) += c[j] * s; leaves the carry out in CC
+  template <class Acc>
+  ZKB_HD static void even_chain(uint32_t* X, Acc c, uint32_t s) {
+    ptx::mad_wide_cc(X[0], X[1], c(0), s);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) ptx::madc_wide_cc(X[j], X[j + 1], c(j), s);
+  }
+  struct ModAcc { ZKB_HD uint32_t operator()(int j) const { return P::mod(j); } };
+  struct ArrAcc { const uint32_t* a; ZKB_HD uint32_t operator()(int j) const { return a[j]; } };
+
+  // One row.  On entry (not first): X = clean even accumulator, Y = previous even
+  // accumulator with Y[0] == 0 and straggler Y[1].  On exit: X[0] == 0, roles swapped.
+  ZKB_HD static void mad_redc_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi, bool first) {
+    if (first) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) ptx::mul_wide(X[j], X[j + 1], a[j], bi);
+#pragma unroll
+      for (int j = 1; j < N; j += 2) ptx::mul_wide(Y[j - 1], Y[j], a[j], bi);
+    } else {
+      X[0] = ptx::add_cc(X[0], Y[1]);
+      // shifted odd chain: new Y = (old Y >> 64) + odd products + carry of the straggler add
+#pragma unroll
+      for (int j = 1; j < N - 1; j += 2) ptx::madc_wide_cc_3(Y[j - 1], Y[j], a[j], bi, Y[j + 1], Y[j + 2]);
+      ptx::madc_wide_cc_3(Y[N - 2], Y[N - 1], a[N - 1], bi, 0, 0);
+      even_chain(X, ArrAcc{a}, bi);
+      Y[N - 1] = ptx::addc(Y[N - 1], 0);          // carry of the even chain has weight 2^(32N)
+    }
+    uint32_t m = ptx::mul_lo(X[0], P::INV);
+    odd_chain(Y, ModAcc{}, m);
+    even_chain(X, ModAcc{}, m);
+    Y[N - 1] = ptx::addc(Y[N - 1], 0);
+  }
+  // result = Y + (X >> 32) after an even number of rows (last row had X = odd array)
+  ZKB_HD static Fp merge_final(const uint32_t* Y, const uint32_t* X) {
+    uint32_t T[N];
+    T[0] = ptx::add_cc(Y[0], X[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) T[k] = ptx::addc_cc(Y[k], X[k + 1]);
+    T[N - 1] = ptx::addc(Y[N - 1], 0);
+    return final_sub(T);
+  }
+  // final conditional subtraction: T (N limbs, < 2p) -> [0, p)
+  ZKB_HD static Fp final_sub(const uint32_t* T) {
+    Fp s, t;
+    t.v[0] = ptx::sub_cc(T[0], P::mod(0));
+#pragma unroll
+    for (int i = 1; i < N; i++) t.v[i] = ptx::subc_cc(T[i], P::mod(i));
+    uint32_t borrow = ptx::subc(0, 0);
+#pragma unroll
+    for (int i = 0; i < N; i++) s.v[i] = borrow ? T[i] : t.v[i];
+    return s;
+  }
+
+  // Montgomery product a * b * R^-1 mod p
+  ZKB_HD static Fp mul(const Fp& a, const Fp& b) {
+    static_assert(N % 2 == 0, "even limb count expected");
+    uint32_t even[N], odd[N];
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      mad_redc_row(even, odd, a.v, b.v[i], i == 0);
+      mad_redc_row(odd, even, a.v, b.v[i + 1], false);
+    }
+    return merge_final(even, odd);
+  }
+  ZKB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+
+  ZKB_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }
+  ZKB_HD static Fp from_mont(const Fp& a) {
+    Fp o = zero();
+    o.v[0] = 1;
+    return mul(a, o);
+  }
+
+  // a^e, e given as N 32-bit limbs through a constexpr accessor (Fermat inversion)
+  ZKB_HD static Fp inv(const Fp& a) {
+    Fp r = one();
+    for (int i = N - 1; i >= 0; i--) {
+      uint32_t e = P::pm2(i);
+      for (int b = 31; b >= 0; b--) {
+        r = sqr(r);
+        if ((e >> b) & 1) r = mul(r, a);
+      }
+    }
+    return r;
+  }
+  // a^e for a runtime 64-bit exponent
+  ZKB_HD static Fp pow_u64(const Fp& a, uint64_t e) {
+    Fp r = one();
+    for (int b = 63; b >= 0; b--) {
+      r = sqr(r);
+      if ((e >> b) & 1) r = mul(r, a);
+    }
+    return r;
+  }
+  ZKB_HD static Fp small(uint32_t k) {  // k as a field element (Montgomery)
+    Fp t = zero();
+    t.v[0] = k;
+    return to_mont(t);
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2+1)   (ark-ff `Fp2` with NONRESIDUE = -1 for both curves)
+// ---------------------------------------------------------------------------------
+template <class P>
+struct Fp2 {
+  using Base = Fp<P>;
+  using Params = P;
+  Base c0, c1;
+
+  ZKB_HD static Fp2 zero() { return {Base::zero(), Base::zero()}; }
+  ZKB_HD static Fp2 one() { return {Base::one(), Base::zero()}; }
+  ZKB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+  ZKB_HD bool operator==(const Fp2& o) const { return c0 == o.c0 && c1 == o.c1; }
+  ZKB_HD bool operator!=(const Fp2& o) const { return !(*this == o); }
+  ZKB_HD static Fp2 add(const Fp2& a, const Fp2& b) { return {Base::add(a.c0, b.c0), Base::add(a.c1, b.c1)}; }
+  ZKB_HD static Fp2 sub(const Fp2& a, const Fp2& b) { return {Base::sub(a.c0, b.c0), Base::sub(a.c1, b.c1)}; }
+  ZKB_HD static Fp2 neg(const Fp2& a) { return {Base::neg(a.c0), Base::neg(a.c1)}; }
+  ZKB_HD static Fp2 dbl(const Fp2& a) { return {Base::dbl(a.c0), Base::dbl(a.c1)}; }
+  ZKB_HD static Fp2 mul(const Fp2& a, const Fp2& b) {
+    // Karatsuba: 3 base multiplications
+    Base t0 = Base::mul(a.c0, b.c0);
+    Base t1 = Base::mul(a.c1, b.c1);
+    Base s = Base::mul(Base::add(a.c0, a.c1), Base::add(b.c0, b.c1));
+    return {Base::sub(t0, t1), Base::sub(Base::sub(s, t0), t1)};
+  }
+  ZKB_HD static Fp2 sqr(const Fp2& a) {
+    // (c0+c1)(c0-c1) + 2 c0 c1 u
+    Base t = Base::mul(a.c0, a.c1);
+    Base r0 = Base::mul(Base::add(a.c0, a.c1), Base::sub(a.c0, a.c1));
+    return {r0, Base::dbl(t)};
+  }
+  ZKB_HD static Fp2 inv(const Fp2& a) {
+    Base n = Base::inv(Base::add(Base::sqr(a.c0), Base::sqr(a.c1)));
+    return {Base::mul(a.c0, n), Base::neg(Base::mul(a.c1, n))};
+  }
+};
+
+}  // namespace zkb

@@ -1,0 +1,338 @@
+// Groth16 prove path on the device, templated on the curve.  Included by one .cu per curve.
+//
+// Follows groth16/src/prover.rs:148-210 and groth16/src/r1cs_to_qap.rs:113-172 step by step;
+// what changes is where each step runs (all of it on the GPU) and that the 1/N of the three
+// inverse transforms and the coset shift of the following forward transforms are applied by
+// the NTT passes themselves (ntt.cu).
+#pragma once
+#include "groth16.cuh"
+#include "devutil.cuh"
+
+namespace zkb {
+
+int fr_convert_dev(zkb_ctx* ctx, cudaStream_t st, int curve, const void* d_in, void* d_out, size_t n, int mode);
+
+// ------------------------------------------------------------------------------------------
+// evaluate_constraint over all rows (r1cs_to_qap.rs:15-52,131-142,155-159): out[i] = <row_i, z>
+// for i < n_rows; for the A matrix rows n_rows .. n_rows + n_inputs - 1 carry z_input[i]
+// (:140-142); everything up to the domain size is zero.  One thread per row: rows hold 1-3
+// terms, adjacent rows are adjacent in memory.
+// ------------------------------------------------------------------------------------------
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_spmv(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx, const Fp<FrP>* __restrict__ coeff,
+       const Fp<FrP>* __restrict__ z, Fp<FrP>* __restrict__ out, uint32_t n_rows, uint32_t n_inputs_tail,
+       uint32_t domain) {
+  using Fr = Fp<FrP>;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= domain) return;
+  Fr acc = Fr::zero();
+  if (i < n_rows) {
+    uint32_t p0 = row_ptr[i], p1 = row_ptr[i + 1];
+    const Fr one = Fr::one();
+    for (uint32_t p = p0; p < p1; p++) {
+      Fr c = ld_vec(&coeff[p]);
+      Fr v = ld_vec(&z[col_idx[p]]);
+      if (c != one) v = Fr::mul(v, c);      // the reference's is_one fast path (r1cs_to_qap.rs:41-45)
+      acc = Fr::add(acc, v);
+    }
+  } else if (i < n_rows + n_inputs_tail) {
+    acc = ld_vec(&z[i - n_rows]);
+  }
+  st_vec(&out[i], acc);
+}
+
+// ab = (a * b - c) * 1/Z(g)   (r1cs_to_qap.rs:150,164-168)
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_qap_pointwise(Fp<FrP>* __restrict__ a, const Fp<FrP>* __restrict__ b, const Fp<FrP>* __restrict__ c,
+                const Fp<FrP>* __restrict__ zinv_p, size_t n) {
+  using Fr = Fp<FrP>;
+  const Fr zinv = *zinv_p;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = Fr::mul(ld_vec_rw(&a[i]), ld_vec_rw(&b[i]));
+    x = Fr::sub(x, ld_vec_rw(&c[i]));
+    st_vec(&a[i], Fr::mul(x, zinv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// proof assembly (prover.rs:164-210)
+// ------------------------------------------------------------------------------------------
+template <class Fq, class Fq2>
+struct G16Results {
+  // MSM outputs
+  XYZZ<Fq> msm_a, msm_b1, msm_h, msm_l;
+  XYZZ<Fq2> msm_b2;
+  // r*delta, s*delta, (r*s)*delta in G1; s*delta in G2
+  XYZZ<Fq> r_delta, s_delta, rs_delta;
+  XYZZ<Fq2> s_delta2;
+  // g_a, g1_b and s*g_a, r*g1_b
+  XYZZ<Fq> g_a, g1_b, s_g_a, r_g1_b;
+  XYZZ<Fq2> g2_b;
+  // proof, canonical affine
+  Affine<Fq> proof_a;
+  Affine<Fq2> proof_b;
+  Affine<Fq> proof_c;
+  uint32_t inf[4];
+};
+
+// scal: [r, s] canonical -> scal[2] = r * s mod p (canonical); four independent scalar
+// multiplications, one warp-lane-0 each in separate blocks
+template <class FrP, class Fq, class Fq2>
+__global__ void k_g16_scalars(Fp<FrP> r, Fp<FrP> s, Fp<FrP>* scal, const Affine<Fq>* g1_singles,
+                              const Affine<Fq2>* g2_singles, G16Results<Fq, Fq2>* res) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x) return;
+  if (blockIdx.x == 0) scal[0] = r;
+  if (blockIdx.x == 1) scal[1] = s;
+  XYZZ<Fq> d1 = XYZZ<Fq>::from_affine(g1_singles[2]);
+  if (blockIdx.x == 0) st_vec(&res->r_delta, XYZZ<Fq>::mul_limbs(d1, r.v, Fr::N));
+  if (blockIdx.x == 1) st_vec(&res->s_delta, XYZZ<Fq>::mul_limbs(d1, s.v, Fr::N));
+  if (blockIdx.x == 2) {
+    Fr rs = Fr::from_mont(Fr::mul(Fr::to_mont(r), Fr::to_mont(s)));
+    scal[2] = rs;
+    st_vec(&res->rs_delta, XYZZ<Fq>::mul_limbs(d1, rs.v, Fr::N));
+  }
+  if (blockIdx.x == 3) {
+    XYZZ<Fq2> d2 = XYZZ<Fq2>::from_affine(g2_singles[1]);
+    st_vec(&res->s_delta2, XYZZ<Fq2>::mul_limbs(d2, s.v, Fr::N));
+  }
+}
+
+// calculate_coeff (prover.rs:213-228): res = initial + query[0] + acc + vk_param, for A, B-G1, B-G2;
+// then s*g_a and r*g1_b (prover.rs:192-193)
+template <class FrP, class Fq, class Fq2>
+__global__ void k_g16_coeffs(const Fp<FrP>* scal, const Affine<Fq>* a0, const Affine<Fq>* b1_0, const Affine<Fq2>* b2_0,
+                             const Affine<Fq>* g1_singles, const Affine<Fq2>* g2_singles, G16Results<Fq, Fq2>* res) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x) return;
+  Fr r = scal[0], s = scal[1];
+  if (blockIdx.x == 0) {
+    XYZZ<Fq> g = ld_vec_rw(&res->r_delta);
+    g.madd(*a0);
+    g.add(ld_vec_rw(&res->msm_a));
+    g.madd(g1_singles[0]);               // alpha_g1
+    st_vec(&res->g_a, g);
+    st_vec(&res->s_g_a, XYZZ<Fq>::mul_limbs(g, s.v, Fr::N));
+  }
+  if (blockIdx.x == 1) {
+    XYZZ<Fq> g = XYZZ<Fq>::inf();
+    if (!r.is_zero()) {                  // the guard is on r (prover.rs:170)
+      g = ld_vec_rw(&res->s_delta);
+      g.madd(*b1_0);
+      g.add(ld_vec_rw(&res->msm_b1));
+      g.madd(g1_singles[1]);             // beta_g1
+    }
+    st_vec(&res->g1_b, g);
+    st_vec(&res->r_g1_b, XYZZ<Fq>::mul_limbs(g, r.v, Fr::N));
+  }
+  if (blockIdx.x == 2) {
+    XYZZ<Fq2> g = ld_vec_rw(&res->s_delta2);
+    g.madd(*b2_0);
+    g.add(ld_vec_rw(&res->msm_b2));
+    g.madd(g2_singles[0]);               // beta_g2
+    st_vec(&res->g2_b, g);
+  }
+}
+
+// g_c = s*g_a + r*g1_b - r*s*delta + l_acc + h_acc; into_affine of (g_a, g2_b, g_c)  (prover.rs:195-210)
+template <class Fq, class Fq2>
+__global__ void k_g16_finish(G16Results<Fq, Fq2>* res) {
+  if (threadIdx.x) return;
+  if (blockIdx.x == 0) {
+    XYZZ<Fq> g = ld_vec_rw(&res->g_a);
+    st_vec(&res->proof_a, g.to_affine());
+    res->inf[0] = g.is_inf();
+  }
+  if (blockIdx.x == 1) {
+    XYZZ<Fq2> g = ld_vec_rw(&res->g2_b);
+    st_vec(&res->proof_b, g.to_affine());
+    res->inf[1] = g.is_inf();
+  }
+  if (blockIdx.x == 2) {
+    XYZZ<Fq> g = ld_vec_rw(&res->s_g_a);
+    g.add(ld_vec_rw(&res->r_g1_b));
+    XYZZ<Fq> d = ld_vec_rw(&res->rs_delta);
+    d.neg_in_place();
+    g.add(d);
+    g.add(ld_vec_rw(&res->msm_l));
+    g.add(ld_vec_rw(&res->msm_h));
+    st_vec(&res->proof_c, g.to_affine());
+    res->inf[2] = g.is_inf();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+template <class FrP, class FqP, int CURVE>
+struct Groth16Impl {
+  using Fr = Fp<FrP>;
+  using Fq = Fp<FqP>;
+  using Fq2 = Fp2<FqP>;
+  using Res = G16Results<Fq, Fq2>;
+
+  static int ensure(zkb_ctx* ctx, DevBuf* b, size_t bytes) {
+    if (b->p && b->cap >= bytes) return ZKB_OK;
+    if (b->p) ZKB_CUDA(ctx, cudaFree(b->p));
+    b->p = nullptr;
+    b->cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    ZKB_CUDA(ctx, cudaMalloc(&b->p, want));
+    b->cap = want;
+    return ZKB_OK;
+  }
+
+  static int upload_csr(zkb_ctx* ctx, cudaStream_t st, DevCsr* d, const zkb_csr* h) {
+    if ((h->n_rows && !h->row_ptr) || (h->nnz && (!h->col_idx || !h->coeff_mont)))
+      return set_err(ctx, ZKB_E_INVALID, "groth16: null matrix");
+    if (h->n_rows >= (size_t(1) << 31) || h->nnz >= (size_t(1) << 32))
+      return set_err(ctx, ZKB_E_INVALID, "groth16: matrix too large");
+    ZKB_TRY(ensure(ctx, &d->row_ptr, (h->n_rows + 1) * 4));
+    ZKB_TRY(ensure(ctx, &d->col_idx, h->nnz * 4));
+    ZKB_TRY(ensure(ctx, &d->coeff, h->nnz * sizeof(Fr)));
+    d->n_rows = h->n_rows;
+    d->nnz = h->nnz;
+    if (h->n_rows)
+      ZKB_CUDA(ctx, cudaMemcpyAsync(d->row_ptr.p, h->row_ptr, (h->n_rows + 1) * 4, cudaMemcpyHostToDevice, st));
+    else
+      ZKB_CUDA(ctx, cudaMemsetAsync(d->row_ptr.p, 0, 4, st));
+    if (h->nnz) {
+      ZKB_CUDA(ctx, cudaMemcpyAsync(d->col_idx.p, h->col_idx, h->nnz * 4, cudaMemcpyHostToDevice, st));
+      ZKB_CUDA(ctx, cudaMemcpyAsync(d->coeff.p, h->coeff_mont, h->nnz * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    }
+    return ZKB_OK;
+  }
+
+  static int stage(zkb_ctx* ctx, const zkb_pk*, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                   const uint64_t* z_mont, size_t n_inputs, size_t n_aux) {
+    if (!ctx->stage) ctx->stage = new Groth16Stage();
+    Groth16Stage* s = ctx->stage;
+    s->staged = false;
+    if (!A || !B || !C || !z_mont) return set_err(ctx, ZKB_E_INVALID, "groth16: null argument");
+    if (A->n_rows != B->n_rows || A->n_rows != C->n_rows)
+      return set_err(ctx, ZKB_E_INVALID, "groth16: A, B, C row counts differ");
+    if (n_inputs == 0) return set_err(ctx, ZKB_E_INVALID, "groth16: input 0 (ONE) missing");
+    // domain = EvaluationDomain::new(num_constraints + num_inputs)  (r1cs_to_qap.rs:123-126)
+    size_t need = A->n_rows + n_inputs;
+    unsigned log_n = ceil_log2(need);
+    if ((int)log_n > FrP::TWO_ADICITY || log_n > 30)
+      return set_err(ctx, ZKB_E_TOO_LARGE, "groth16: domain 2^%u exceeds the field's 2-adicity", log_n);
+    cudaStream_t st = ctx->main;
+    s->curve = CURVE;
+    s->n_inputs = n_inputs; s->n_aux = n_aux; s->n_rows = A->n_rows;
+    s->log_n = log_n; s->N = size_t(1) << log_n;
+    size_t nz = n_inputs + n_aux;
+    ZKB_TRY(ensure(ctx, &s->z, nz * sizeof(Fr)));
+    ZKB_TRY(ensure(ctx, &s->z_repr, nz * sizeof(Fr)));
+    ZKB_TRY(ensure(ctx, &s->va, s->N * sizeof(Fr)));
+    ZKB_TRY(ensure(ctx, &s->vb, s->N * sizeof(Fr)));
+    ZKB_TRY(ensure(ctx, &s->vc, s->N * sizeof(Fr)));
+    ZKB_TRY(ensure(ctx, &s->scratch, s->N * sizeof(Fr)));
+    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, sizeof(Res)));
+    if (!s->scal) ZKB_CUDA(ctx, cudaMalloc(&s->scal, sizeof(Fr) * 4));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(s->z.p, z_mont, nz * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKB_TRY(upload_csr(ctx, st, &s->A, A));
+    ZKB_TRY(upload_csr(ctx, st, &s->B, B));
+    ZKB_TRY(upload_csr(ctx, st, &s->C, C));
+    s->staged = true;
+    return ZKB_OK;
+  }
+
+  // witness_map + into_repr: h (canonical) ends up in stage->va
+  static int compute_h(zkb_ctx* ctx, cudaStream_t st) {
+    Groth16Stage* s = ctx->stage;
+    if (!s || !s->staged || s->curve != CURVE) return set_err(ctx, ZKB_E_INVALID, "groth16: nothing staged");
+    NttDomain* dom;
+    ZKB_TRY(ntt_get_domain(ctx, CURVE, s->log_n, &dom));
+    const uint32_t N = (uint32_t)s->N;
+    Fr *a = (Fr*)s->va.p, *b = (Fr*)s->vb.p, *c = (Fr*)s->vc.p;
+    const unsigned blocks = ceil_div(N, 256);
+    ZKB_LAUNCH(ctx, (k_spmv<FrP>), blocks, 256, 0, st, (const uint32_t*)s->A.row_ptr.p, (const uint32_t*)s->A.col_idx.p,
+               (const Fr*)s->A.coeff.p, (const Fr*)s->z.p, a, (uint32_t)s->n_rows, (uint32_t)s->n_inputs, N);
+    ZKB_LAUNCH(ctx, (k_spmv<FrP>), blocks, 256, 0, st, (const uint32_t*)s->B.row_ptr.p, (const uint32_t*)s->B.col_idx.p,
+               (const Fr*)s->B.coeff.p, (const Fr*)s->z.p, b, (uint32_t)s->n_rows, 0u, N);
+    ZKB_LAUNCH(ctx, (k_spmv<FrP>), blocks, 256, 0, st, (const uint32_t*)s->C.row_ptr.p, (const uint32_t*)s->C.col_idx.p,
+               (const Fr*)s->C.coeff.p, (const Fr*)s->z.p, c, (uint32_t)s->n_rows, 0u, N);
+    Fr* vecs[3] = {a, b, c};
+    for (int v = 0; v < 3; v++) {
+      ZKB_TRY(ntt_run(ctx, st, dom, vecs[v], s->scratch.p, ZKB_NTT_INVERSE));   // ifft_in_place       (:144-145,161)
+      ZKB_TRY(ntt_run(ctx, st, dom, vecs[v], s->scratch.p, ZKB_NTT_COSET));     // coset_fft_in_place  (:147-148,162)
+    }
+    unsigned pw_blocks = blocks > (unsigned)ctx->sm_count * 8 ? ctx->sm_count * 8 : blocks;
+    ZKB_LAUNCH(ctx, (k_qap_pointwise<FrP>), pw_blocks, 256, 0, st, a, (const Fr*)b, (const Fr*)c,
+               (const Fr*)dom->consts + kConstZInv, (size_t)N);
+    ZKB_TRY(ntt_run(ctx, st, dom, a, s->scratch.p, ZKB_NTT_INVERSE | ZKB_NTT_COSET));   // coset_ifft_in_place (:169)
+    ZKB_TRY(fr_convert_dev(ctx, st, CURVE, a, a, N, 0));                                // into_repr (prover.rs:161)
+    return ZKB_OK;
+  }
+
+  static int fetch_h(zkb_ctx* ctx, uint64_t* h) {
+    Groth16Stage* s = ctx->stage;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(h, s->va.p, s->N * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->main));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return ZKB_OK;
+  }
+
+  static int prove_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t* r, const uint64_t* sc) {
+    Groth16Stage* s = ctx->stage;
+    if (!s || !s->staged || s->curve != CURVE) return set_err(ctx, ZKB_E_INVALID, "groth16: nothing staged");
+    if (!pk || pk->curve != CURVE || pk->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "groth16: bad proving key");
+    if (!r || !sc) return set_err(ctx, ZKB_E_INVALID, "groth16: null r/s");
+    cudaStream_t st = ctx->main;
+    const GroupOps* g1 = group_ops(CURVE, ZKB_G1);
+    const GroupOps* g2 = group_ops(CURVE, ZKB_G2);
+    Res* res = (Res*)s->results;
+    Fr* scal = (Fr*)s->scal;
+    if (pk->a->n == 0 || pk->b_g1->n == 0 || pk->b_g2->n == 0)
+      return set_err(ctx, ZKB_E_INVALID, "groth16: empty query (index 0 is read by calculate_coeff)");
+    Fr r_val, s_val;      // by-value kernel arguments: no staging buffer to race on
+    memcpy(r_val.v, r, 32);
+    memcpy(s_val.v, sc, 32);
+    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, st, r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
+               (const Affine<Fq2>*)pk->g2_singles, res);
+    // assignment = into_repr(input[1..] ++ aux)  (prover.rs:150-158)
+    const size_t n_assign = s->n_inputs - 1 + s->n_aux;
+    ZKB_TRY(fr_convert_dev(ctx, st, CURVE, (const Fr*)s->z.p + 1, s->z_repr.p, n_assign, 0));
+    const uint32_t* zr = (const uint32_t*)s->z_repr.p;
+    auto clamp = [](size_t n, const zkb_srs* srs, size_t off) { size_t a = srs->n > off ? srs->n - off : 0; return n < a ? n : a; };
+    ZKB_TRY(g1->msm_run(ctx, st, pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
+    ZKB_TRY(g1->msm_run(ctx, st, pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
+    ZKB_TRY(g2->msm_run(ctx, st, pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
+    ZKB_TRY(g1->msm_run(ctx, st, pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    ZKB_TRY(compute_h(ctx, st));
+    ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
+    ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, st, (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
+               (const Affine<Fq>*)pk->b_g1->table, (const Affine<Fq2>*)pk->b_g2->table,
+               (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles, res);
+    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 3, 32, 0, st, res);
+    return ZKB_OK;
+  }
+
+  static int fetch_proof(zkb_ctx* ctx, const zkb_pk*, uint64_t* proof_xy, uint8_t* proof_inf) {
+    Groth16Stage* s = ctx->stage;
+    if (!s || !s->results) return set_err(ctx, ZKB_E_INVALID, "groth16: no proof computed");
+    cudaStream_t st = ctx->main;
+    Res* res = (Res*)s->results;
+    constexpr size_t kProofBytes = 2 * sizeof(Affine<Fq>) + sizeof(Affine<Fq2>);
+    static_assert(offsetof(Res, proof_b) - offsetof(Res, proof_a) == sizeof(Affine<Fq>), "proof layout");
+    static_assert(offsetof(Res, proof_c) - offsetof(Res, proof_b) == sizeof(Affine<Fq2>), "proof layout");
+    static_assert(offsetof(Res, inf) - offsetof(Res, proof_a) == kProofBytes, "proof layout");
+    char* bounce = (char*)ctx->pinned;
+    ZKB_CUDA(ctx, cudaMemcpyAsync(bounce, &res->proof_a, kProofBytes + 16, cudaMemcpyDeviceToHost, st));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(proof_xy, bounce, kProofBytes);
+    const uint32_t* inf = (const uint32_t*)(bounce + kProofBytes);
+    for (int i = 0; i < 3; i++) proof_inf[i] = inf[i] ? 1 : 0;
+    return ZKB_OK;
+  }
+
+  static const Groth16Ops* ops() {
+    static const Groth16Ops o = {&stage, &compute_h, &prove_staged, &fetch_proof, &fetch_h,
+                                 sizeof(Affine<Fq>), sizeof(Affine<Fq2>)};
+    return &o;
+  }
+};
+
+}  // namespace zkb

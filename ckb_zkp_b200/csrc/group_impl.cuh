@@ -1,0 +1,43 @@
+// Instantiates the MSM engine for one (coordinate field, scalar field) pair and exposes it
+// through the type-erased GroupOps table.  Included by exactly one .cu file per group so the
+// four heavy instantiations compile in parallel.
+#pragma once
+#include "msm.cuh"
+
+namespace zkb {
+
+// out[i] = scalars[i] * base (double-and-add per thread), canonical affine output
+template <class F>
+__global__ void __launch_bounds__(128)
+k_fixed_base_mul(const Affine<F>* __restrict__ base, const uint32_t* __restrict__ scalars, uint32_t n,
+                 Affine<F>* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  XYZZ<F> p = XYZZ<F>::from_affine(ld_vec_rw(base));
+  uint32_t k[kScalarLimbs];
+#pragma unroll
+  for (int j = 0; j < kScalarLimbs; j++) k[j] = scalars[(size_t)i * kScalarLimbs + j];
+  XYZZ<F> r = XYZZ<F>::mul_limbs(p, k, kScalarLimbs);
+  Affine<F> a = r.to_affine();
+  st_vec(&out_xy[i], a);
+  out_inf[i] = r.is_inf() ? 1 : 0;
+}
+
+template <class F, class FrP>
+struct GroupImpl {
+  using E = MsmEngine<F, FrP>;
+  static int fixed_base_mul(zkb_ctx* ctx, cudaStream_t st, const void* d_base, const uint32_t* d_scalars, size_t n,
+                            void* d_out, uint8_t* d_inf) {
+    if (n == 0) return ZKB_OK;
+    ZKB_LAUNCH(ctx, (k_fixed_base_mul<F>), ceil_div(n, 128), 128, 0, st, (const Affine<F>*)d_base, d_scalars,
+               (uint32_t)n, (Affine<F>*)d_out, d_inf);
+    return ZKB_OK;
+  }
+  static const GroupOps* ops() {
+    static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host,
+                               &fixed_base_mul};
+    return &o;
+  }
+};
+
+}  // namespace zkb

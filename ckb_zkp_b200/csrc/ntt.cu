@@ -1,0 +1,198 @@
+// Radix-2 NTT kernels and domain tables -- see ntt.cuh for the design.
+#include "ntt.cuh"
+
+#include "devutil.cuh"
+
+namespace zkb {
+
+constexpr unsigned kTileLog = 10;          // elements per shared-memory tile = 1024
+constexpr unsigned kMinRunLog = 2;         // later passes read >= 4 contiguous elements (128 B)
+
+template <class FrP>
+__global__ void k_domain_consts(unsigned log_n, Fp<FrP>* c) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x | blockIdx.x) return;
+  Fr w, g, gi;
+#pragma unroll
+  for (int i = 0; i < Fr::N; i++) { w.v[i] = FrP::root(i); g.v[i] = FrP::gen(i); gi.v[i] = FrP::gen_inv(i); }
+  for (unsigned i = log_n; i < (unsigned)FrP::TWO_ADICITY; i++) w = Fr::sqr(w);
+  Fr two = Fr::add(Fr::one(), Fr::one());
+  Fr n = Fr::one(), gn = g;
+  for (unsigned i = 0; i < log_n; i++) { n = Fr::mul(n, two); gn = Fr::sqr(gn); }
+  c[kConstOmega] = w;
+  c[kConstOmegaInv] = Fr::inv(w);
+  c[kConstNInv] = Fr::inv(n);
+  c[kConstG] = g;
+  c[kConstGInv] = gi;
+  c[kConstZInv] = Fr::inv(Fr::sub(gn, Fr::one()));   // 1 / Z(g), Z = x^n - 1 (r1cs_to_qap.rs:168)
+  c[kConstGInvScaled] = Fr::zero();
+}
+
+// out[i] = scale * base^i
+template <class FrP>
+__global__ void k_powers(Fp<FrP>* out, size_t count, const Fp<FrP>* base_p, const Fp<FrP>* scale_p) {
+  using Fr = Fp<FrP>;
+  constexpr int CH = 32;
+  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CH;
+  if (i0 >= count) return;
+  Fr base = *base_p;
+  Fr cur = Fr::pow_u64(base, (uint64_t)i0);
+  if (scale_p) cur = Fr::mul(cur, *scale_p);
+  for (int k = 0; k < CH && i0 + k < count; k++) {
+    st_vec(&out[i0 + k], cur);
+    cur = Fr::mul(cur, base);
+  }
+}
+
+// One DIT pass: stages s0 .. s0+k-1 on tiles of 2^(k+t) elements.
+//   element e of a tile: lo = e & (2^t - 1), mid = e >> t
+//   global index        = (hi << (s0 + k)) | (mid << s0) | (lo_base + lo)
+template <class FrP>
+__global__ void __launch_bounds__(512)
+k_ntt_pass(const Fp<FrP>* src, Fp<FrP>* dst, const Fp<FrP>* __restrict__ tw, unsigned log_n, unsigned s0, unsigned k,
+           unsigned t, int first, const Fp<FrP>* __restrict__ pre_scale, const Fp<FrP>* __restrict__ post_scale,
+           const Fp<FrP>* __restrict__ post_const) {
+  using Fr = Fp<FrP>;
+  extern __shared__ uint32_t sm[];
+  const unsigned E = 1u << (k + t);
+  const unsigned lo_groups_log = s0 - t;                       // tiles per hi value = 2^(s0 - t)
+  const size_t tile = blockIdx.x;
+  const size_t hi = tile >> lo_groups_log;
+  const size_t lo_base = (tile & ((size_t(1) << lo_groups_log) - 1)) << t;
+  const unsigned lo_mask = (1u << t) - 1;
+
+  for (unsigned e = threadIdx.x; e < E; e += blockDim.x) {
+    size_t idx = (hi << (s0 + k)) | ((size_t)(e >> t) << s0) | (lo_base + (e & lo_mask));
+    size_t sidx = idx;
+    if (first) sidx = (size_t)(__brevll((unsigned long long)idx) >> (64 - log_n));
+    Fr v = ld_vec_rw(&src[sidx]);
+    if (pre_scale) v = Fr::mul(v, ld_vec(&pre_scale[sidx]));
+#pragma unroll
+    for (int w = 0; w < Fr::N; w++) sm[w * E + e] = v.v[w];
+  }
+  __syncthreads();
+
+  for (unsigned q = 0; q < k; q++) {
+    for (unsigned i = threadIdx.x; i < E / 2; i += blockDim.x) {
+      unsigned lo = i & lo_mask, m = i >> t;
+      unsigned mid0 = ((m >> q) << (q + 1)) | (m & ((1u << q) - 1));
+      unsigned e0 = (mid0 << t) | lo, e1 = e0 + (1u << (q + t));
+      size_t j = ((size_t)(mid0 & ((1u << q) - 1)) << s0) | (lo_base + lo);   // index inside the 2^(s0+q) half-group
+      Fr w = ld_vec(&tw[j << (log_n - 1 - (s0 + q))]);
+      Fr a, b;
+#pragma unroll
+      for (int x = 0; x < Fr::N; x++) { a.v[x] = sm[x * E + e0]; b.v[x] = sm[x * E + e1]; }
+      b = Fr::mul(b, w);
+      Fr s = Fr::add(a, b), d = Fr::sub(a, b);
+#pragma unroll
+      for (int x = 0; x < Fr::N; x++) { sm[x * E + e0] = s.v[x]; sm[x * E + e1] = d.v[x]; }
+    }
+    __syncthreads();
+  }
+
+  Fr pc;
+  if (post_const) pc = *post_const;
+  for (unsigned e = threadIdx.x; e < E; e += blockDim.x) {
+    size_t idx = (hi << (s0 + k)) | ((size_t)(e >> t) << s0) | (lo_base + (e & lo_mask));
+    Fr v;
+#pragma unroll
+    for (int w = 0; w < Fr::N; w++) v.v[w] = sm[w * E + e];
+    if (post_scale) v = Fr::mul(v, ld_vec(&post_scale[idx]));
+    if (post_const) v = Fr::mul(v, pc);
+    st_vec(&dst[idx], v);
+  }
+}
+
+template <class FrP>
+static int build_domain(zkb_ctx* ctx, NttDomain* d) {
+  using Fr = Fp<FrP>;
+  cudaStream_t st = ctx->main;
+  size_t n = d->n, half = n > 1 ? n / 2 : 1;
+  ZKB_CUDA(ctx, cudaMalloc(&d->consts, sizeof(Fr) * kNumConsts));
+  ZKB_CUDA(ctx, cudaMalloc(&d->tw, sizeof(Fr) * half));
+  ZKB_CUDA(ctx, cudaMalloc(&d->tw_inv, sizeof(Fr) * half));
+  ZKB_CUDA(ctx, cudaMalloc(&d->coset, sizeof(Fr) * n));
+  ZKB_CUDA(ctx, cudaMalloc(&d->coset_inv, sizeof(Fr) * n));
+  Fr* c = (Fr*)d->consts;
+  ZKB_LAUNCH(ctx, (k_domain_consts<FrP>), 1, 32, 0, st, d->log_n, c);
+  ZKB_LAUNCH(ctx, (k_powers<FrP>), ceil_div(ceil_div(half, 32), 128), 128, 0, st, (Fr*)d->tw, half, c + kConstOmega, (const Fr*)nullptr);
+  ZKB_LAUNCH(ctx, (k_powers<FrP>), ceil_div(ceil_div(half, 32), 128), 128, 0, st, (Fr*)d->tw_inv, half, c + kConstOmegaInv, (const Fr*)nullptr);
+  ZKB_LAUNCH(ctx, (k_powers<FrP>), ceil_div(ceil_div(n, 32), 128), 128, 0, st, (Fr*)d->coset, n, c + kConstG, (const Fr*)nullptr);
+  ZKB_LAUNCH(ctx, (k_powers<FrP>), ceil_div(ceil_div(n, 32), 128), 128, 0, st, (Fr*)d->coset_inv, n, c + kConstGInv, c + kConstNInv);
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+int ntt_get_domain(zkb_ctx* ctx, int curve, unsigned log_n, NttDomain** out) {
+  int two_adicity = curve == ZKB_BLS12_381 ? BlsFr::TWO_ADICITY : BnFr::TWO_ADICITY;
+  if ((int)log_n > two_adicity) return set_err(ctx, ZKB_E_TOO_LARGE, "domain 2^%u exceeds the field's 2-adicity %d", log_n, two_adicity);
+  if (log_n > 30) return set_err(ctx, ZKB_E_TOO_LARGE, "domain 2^%u not supported", log_n);
+  int key = curve * 64 + (int)log_n;
+  auto it = ctx->domains.find(key);
+  if (it != ctx->domains.end()) { *out = it->second; return ZKB_OK; }
+  NttDomain* d = new NttDomain();
+  d->curve = curve; d->log_n = log_n; d->n = size_t(1) << log_n;
+  d->tw = d->tw_inv = d->coset = d->coset_inv = d->consts = nullptr;
+  int rc = curve == ZKB_BLS12_381 ? build_domain<BlsFr>(ctx, d) : build_domain<BnFr>(ctx, d);
+  if (rc != ZKB_OK) { delete d; return rc; }
+  ctx->domains[key] = d;
+  *out = d;
+  return ZKB_OK;
+}
+
+void ntt_free_domains(zkb_ctx* ctx) {
+  for (auto& kv : ctx->domains) {
+    NttDomain* d = kv.second;
+    cudaFree(d->tw); cudaFree(d->tw_inv); cudaFree(d->coset); cudaFree(d->coset_inv); cudaFree(d->consts);
+    delete d;
+  }
+  ctx->domains.clear();
+}
+
+template <class FrP>
+static int ntt_run_t(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data, void* d_scratch, unsigned flags) {
+  using Fr = Fp<FrP>;
+  const unsigned log_n = dom->log_n;
+  const bool inverse = flags & ZKB_NTT_INVERSE, coset = flags & ZKB_NTT_COSET;
+  Fr* data = (Fr*)d_data;
+  Fr* scratch = (Fr*)d_scratch;
+  const Fr* tw = (const Fr*)(inverse ? dom->tw_inv : dom->tw);
+  const Fr* pre = (coset && !inverse) ? (const Fr*)dom->coset : nullptr;
+  const Fr* post = (coset && inverse) ? (const Fr*)dom->coset_inv : nullptr;
+  const Fr* pconst = (inverse && !coset) ? (const Fr*)dom->consts + kConstNInv : nullptr;
+  if (log_n == 0) return ZKB_OK;      // size-1 transform is the identity (g^0 = 1, 1/1 = 1)
+
+  // plan the passes
+  unsigned ks[8], np = 0;
+  unsigned k1 = log_n < kTileLog ? log_n : kTileLog;
+  ks[np++] = k1;
+  unsigned rem = log_n - k1;
+  if (rem) {
+    unsigned kmax = kTileLog - kMinRunLog;
+    unsigned cnt = (rem + kmax - 1) / kmax;
+    for (unsigned i = 0; i < cnt; i++) ks[np++] = rem / cnt + (i < rem % cnt ? 1 : 0);
+  }
+  unsigned s0 = 0;
+  for (unsigned p = 0; p < np; p++) {
+    unsigned k = ks[p];
+    unsigned t = p == 0 ? 0 : kTileLog - k;
+    unsigned E = 1u << (k + t);
+    const Fr* src = p == 0 ? data : scratch;
+    Fr* dst = (p == np - 1 && np > 1) ? data : scratch;
+    unsigned threads = E / 2 < 32 ? 32 : E / 2;
+    size_t tiles = dom->n >> (k + t);
+    ZKB_LAUNCH(ctx, (k_ntt_pass<FrP>), (unsigned)tiles, threads, sizeof(uint32_t) * Fr::N * E, st, src, dst, tw, log_n, s0, k,
+               t, p == 0 ? 1 : 0, p == 0 ? pre : (const Fr*)nullptr, p == np - 1 ? post : (const Fr*)nullptr,
+               p == np - 1 ? pconst : (const Fr*)nullptr);
+    s0 += k;
+  }
+  if (np == 1) ZKB_CUDA(ctx, cudaMemcpyAsync(data, scratch, sizeof(Fr) * dom->n, cudaMemcpyDeviceToDevice, st));
+  return ZKB_OK;
+}
+
+int ntt_run(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data, void* d_scratch, unsigned flags) {
+  return dom->curve == ZKB_BLS12_381 ? ntt_run_t<BlsFr>(ctx, st, dom, d_data, d_scratch, flags)
+                                     : ntt_run_t<BnFr>(ctx, st, dom, d_data, d_scratch, flags);
+}
+
+}  // namespace zkb

@@ -1,0 +1,167 @@
+/*
+ * zkb.h -- C ABI of the B200 proving backend for ckb-zkp's Groth16 / Marlin prove path.
+ *
+ * The reference (sec-bit/ckb-zkp @ 8f2141a) has no FFI: its "interface" for this path is
+ * Rust generics resolved at compile time.  Each entry point below replaces one of those
+ * call sites; INTEGRATION.md shows the Rust `extern "C"` binding and the patched bodies.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative ZKB_E_* code; never throws/aborts;
+ *     zkb_last_error() gives a human-readable message for the calling ctx.
+ *   - caller owns all host buffers; the library owns device memory behind opaque handles.
+ *   - field elements: little-endian u64 limbs exactly as ark-ff 0.2 stores them
+ *     (Fr: 4 limbs for both curves; Fq: 4 limbs BN254, 6 limbs BLS12-381).
+ *       "mont"      = Montgomery form, R = 2^(64*limbs)  (the in-memory form of `Fp256/Fp384`)
+ *       "canonical" = plain integer < modulus             (the form `into_repr()` yields)
+ *   - affine points: x || y in Montgomery form (Fq2 = c0 || c1), plus one infinity byte per
+ *     point (ark `GroupAffine { x, y, infinity }` marshalled once at upload).  All group
+ *     results are returned as canonical-form affine points, so byte compare == group equality.
+ *   - one ctx per GPU per host thread (internally serialised).
+ */
+#ifndef ZKB_H
+#define ZKB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZKB_BN254 0
+#define ZKB_BLS12_381 1
+#define ZKB_G1 1
+#define ZKB_G2 2
+
+#define ZKB_OK 0
+#define ZKB_E_INVALID (-1)   /* bad argument (null pointer, unknown curve, size overflow)     */
+#define ZKB_E_CUDA (-2)      /* CUDA runtime error; see zkb_last_error                         */
+#define ZKB_E_TOO_LARGE (-3) /* domain larger than the field's 2-adicity:
+                                SynthesisError::PolynomialDegreeTooLarge (r1cs/src/error.rs:15) */
+#define ZKB_E_NO_DEVICE (-4) /* no usable CUDA device: there is no CPU fallback                */
+
+/* zkb_ntt flags */
+#define ZKB_NTT_INVERSE 1u   /* ifft_in_place:  includes the 1/N scaling                       */
+#define ZKB_NTT_COSET 2u     /* coset_fft / coset_ifft with g = Fr::multiplicative_generator() */
+
+/* zkb_srs_upload flags */
+#define ZKB_SRS_PRECOMPUTE 1u /* keep 2^(c*j) * P_i for every window j resident in HBM          */
+
+typedef struct zkb_ctx zkb_ctx;
+typedef struct zkb_srs zkb_srs;
+typedef struct zkb_pk zkb_pk;
+
+/* Sparse matrix in CSR form: the flattening of ProvingAssignment::{at,bt,ct}
+ * (groth16/src/prover.rs:16-25): row i holds (coeff, column) pairs with
+ * column = Input(i) -> i, Aux(i) -> num_inputs + i (groth16/src/r1cs_to_qap.rs:34-37).
+ * Duplicate columns inside a row are allowed (r1cs/src/impl_lc.rs:58-70). */
+typedef struct zkb_csr {
+  size_t n_rows;
+  size_t nnz;
+  const uint32_t* row_ptr;   /* n_rows + 1 */
+  const uint32_t* col_idx;   /* nnz */
+  const uint64_t* coeff_mont;/* nnz * 4 limbs, Montgomery */
+} zkb_csr;
+
+/* ---- context ------------------------------------------------------------------------- */
+int zkb_init(int device, zkb_ctx** out);
+void zkb_destroy(zkb_ctx* ctx);
+const char* zkb_last_error(zkb_ctx* ctx);
+/* cudaStream_t of the ctx's main stream (for callers that time with CUDA events). */
+void* zkb_stream(zkb_ctx* ctx);
+int zkb_sync(zkb_ctx* ctx);
+/* number of kernels this ctx has launched so far (bench.py's `gpu_launches`). */
+uint64_t zkb_launch_count(zkb_ctx* ctx);
+
+/* ---- bases resident in HBM --------------------------------------------------------------
+ * Replaces the `&[G::Affine]` argument of ark_ec::msm::VariableBaseMSM::multi_scalar_mul
+ * (call sites groth16/src/prover.rs:187,190,220; marlin/src/pc/kzg10.rs:109,118,137,146;
+ * curve/src/lib.rs:44).  Uploaded once per Parameters / CommitterKey, reused by every proof. */
+int zkb_srs_upload(zkb_ctx* ctx, int curve, int group, const uint64_t* xy_mont, const uint8_t* inf,
+                   size_t n, unsigned flags, zkb_srs** out);
+void zkb_srs_free(zkb_srs* srs);
+size_t zkb_srs_len(const zkb_srs* srs);
+
+/* ---- variable-base MSM --------------------------------------------------------------------
+ * VariableBaseMSM::multi_scalar_mul(&bases[base_offset..base_offset+n], &scalars[..n]).
+ * scalars: n * 4 limbs, canonical (what `into_repr()` produced in prover.rs:150-161).
+ * out_xy: one affine point (Montgomery), out_inf: 1 if the result is the identity. */
+int zkb_msm(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars_canonical,
+            size_t n, uint64_t* out_xy, uint8_t* out_inf);
+/* Curve::vartime_multiscalar_mul (curve/src/lib.rs:38-45): scalars in Montgomery form,
+ * `into_repr` is fused on the device. */
+int zkb_msm_mont(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars_mont,
+                 size_t n, uint64_t* out_xy, uint8_t* out_inf);
+/* Same, with the scalars already in device memory (device pointer) -- used to time the
+ * kernel path alone. */
+int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void* d_scalars_canonical,
+                size_t n, uint64_t* out_xy, uint8_t* out_inf);
+
+/* ---- radix-2 NTT over Fr --------------------------------------------------------------------
+ * EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place of ark-poly 0.2 as used in
+ * groth16/src/r1cs_to_qap.rs:144-169: natural order in and out, 2^log_n elements of 4 limbs
+ * in Montgomery form, in place. */
+int zkb_ntt(zkb_ctx* ctx, int curve, uint64_t* data_mont, unsigned log_n, unsigned flags);
+int zkb_ntt_dev(zkb_ctx* ctx, int curve, void* d_data_mont, unsigned log_n, unsigned flags);
+
+/* ---- Groth16 ------------------------------------------------------------------------------ */
+/* R1CStoQAP::witness_map (groth16/src/r1cs_to_qap.rs:113-172) followed by the into_repr sweep
+ * of prover.rs:161.  z_mont = input_assignment ++ aux_assignment (n_inputs + n_aux elements,
+ * z[0] = ONE).  h_canonical receives next_pow2(n_rows + n_inputs) * 4 limbs. */
+int zkb_groth16_h(zkb_ctx* ctx, int curve, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                  const uint64_t* z_mont, size_t n_inputs, size_t n_aux, uint64_t* h_canonical);
+
+/* Parameters<E> (groth16/src/lib.rs:81-91) made resident.  Point arrays are x||y Montgomery +
+ * infinity bytes; singles are [alpha_g1, beta_g1, delta_g1] and [beta_g2, delta_g2]. */
+int zkb_groth16_pk_create(zkb_ctx* ctx, int curve,
+                          const uint64_t* a_query, const uint8_t* a_inf, size_t a_len,
+                          const uint64_t* b_g1_query, const uint8_t* b_g1_inf, size_t b_g1_len,
+                          const uint64_t* b_g2_query, const uint8_t* b_g2_inf, size_t b_g2_len,
+                          const uint64_t* h_query, const uint8_t* h_inf, size_t h_len,
+                          const uint64_t* l_query, const uint8_t* l_inf, size_t l_len,
+                          const uint64_t* g1_singles /* alpha, beta, delta */, const uint64_t* g2_singles /* beta, delta */,
+                          zkb_pk** out);
+void zkb_groth16_pk_free(zkb_pk* pk);
+
+/* create_proof (groth16/src/prover.rs:124-211) from "prover filled" (:146) to "Proof assembled"
+ * (:206): witness_map, into_repr, 5 MSMs, final assembly, into_affine.
+ * r, s: 4 limbs each, canonical.  proof_xy = A (G1) || B (G2) || C (G1) affine Montgomery;
+ * proof_inf[3] = infinity flags. */
+int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                      const uint64_t* z_mont, size_t n_inputs, size_t n_aux,
+                      const uint64_t r_canonical[4], const uint64_t s_canonical[4],
+                      uint64_t* proof_xy, uint8_t* proof_inf);
+
+/* Two-phase variant used to time the device path with inputs resident in HBM:
+ * zkb_groth16_stage copies matrices and assignment to the device, zkb_groth16_prove_staged
+ * runs the whole prove path from there (the result stays on the device until
+ * zkb_groth16_fetch_proof). */
+int zkb_groth16_stage(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                      const uint64_t* z_mont, size_t n_inputs, size_t n_aux);
+int zkb_groth16_prove_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t r_canonical[4],
+                             const uint64_t s_canonical[4]);
+int zkb_groth16_fetch_proof(zkb_ctx* ctx, const zkb_pk* pk, uint64_t* proof_xy, uint8_t* proof_inf);
+
+/* ---- fixed-base batch multiplication (setup side; groth16/src/generator.rs:205-256) -------
+ * out[i] = scalars[i] * G for one affine base point G; result-identical to ark FixedBaseMSM
+ * followed by batch_normalization.  Used to mint synthetic SRS on the device. */
+int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_xy_mont,
+                       const uint64_t* scalars_canonical, size_t n, uint64_t* out_xy, uint8_t* out_inf);
+
+/* ---- Fr helpers (device-side batch ops on host arrays; used by the host layers) ------------ */
+/* out[i] = into_repr(in[i]) (mode 0) or from_repr(in[i]) (mode 1) */
+int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode);
+
+/* ---- diagnostics: single field / group operations of the device arithmetic on n operands, used by
+ * the parity tests to check the GPU arithmetic against the CPU oracle in isolation.
+ * field: 0 BN254 Fr, 1 BLS12-381 Fr, 2 BN254 Fq, 3 BLS12-381 Fq.
+ * fp op: 0 mul 1 add 2 sub 3 inv 4 to_mont 5 from_mont 6 sqr 7 neg.
+ * pt op: 0 acc += q (affine, optionally negated) 1 acc += q (XYZZ) 2 dbl 3 to_affine 4 acc * k[8]. */
+int zkb_debug_fp_op(zkb_ctx* ctx, int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out, size_t n);
+int zkb_debug_pt_op(zkb_ctx* ctx, int curve, int group, int op, const uint32_t* acc, const uint32_t* q, int neg,
+                    uint32_t* out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKB_H */

@@ -1,0 +1,83 @@
+// Host-emulation harness: compiles the device headers (field.cuh / curve.cuh) with a
+// host compiler -- ptx.cuh then emulates every carry-chain instruction bit-faithfully --
+// so the exact instruction sequences can be checked against the Python oracle without
+// a GPU.  Test infrastructure only; not linked into the product library.
+#include <cstring>
+#include "../../ckb_zkp_b200/csrc/curve.cuh"
+
+using namespace zkb;
+
+template <class F> static void fp_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  F x, y, r;
+  memcpy(&x, a, sizeof(F));
+  memcpy(&y, b, sizeof(F));
+  switch (op) {
+    case 0: r = F::mul(x, y); break;
+    case 1: r = F::add(x, y); break;
+    case 2: r = F::sub(x, y); break;
+    case 3: r = F::inv(x); break;
+    case 4: r = F::to_mont(x); break;
+    case 5: r = F::from_mont(x); break;
+    case 6: r = F::sqr(x); break;
+    case 7: r = F::neg(x); break;
+    default: r = F::zero();
+  }
+  memcpy(out, &r, sizeof(F));
+}
+
+// op: 0 = acc.madd(q_affine, neg), 1 = acc.add(q_xyzz), 2 = dbl(acc), 3 = to_affine(acc) (out = x,y),
+//     4 = mul_limbs(acc, k[8])
+template <class F> static void pt_op(int op, const uint32_t* acc, const uint32_t* q, int neg, uint32_t* out) {
+  XYZZ<F> a;
+  memcpy(&a, acc, sizeof(a));
+  if (op == 0) {
+    Affine<F> p;
+    memcpy(&p, q, sizeof(p));
+    a.madd(p, neg != 0);
+    memcpy(out, &a, sizeof(a));
+  } else if (op == 1) {
+    XYZZ<F> b;
+    memcpy(&b, q, sizeof(b));
+    a.add(b);
+    memcpy(out, &a, sizeof(a));
+  } else if (op == 2) {
+    a = XYZZ<F>::dbl(a);
+    memcpy(out, &a, sizeof(a));
+  } else if (op == 3) {
+    Affine<F> r = a.to_affine();
+    memcpy(out, &r, sizeof(r));
+  } else if (op == 4) {
+    a = XYZZ<F>::mul_limbs(a, q, 8);
+    memcpy(out, &a, sizeof(a));
+  }
+}
+
+extern "C" {
+// field: 0 BnFr, 1 BlsFr, 2 BnFq, 3 BlsFq, 4 BnFq2, 5 BlsFq2
+void emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  switch (field) {
+    case 0: fp_op<Fp<BnFr>>(op, a, b, out); break;
+    case 1: fp_op<Fp<BlsFr>>(op, a, b, out); break;
+    case 2: fp_op<Fp<BnFq>>(op, a, b, out); break;
+    case 3: fp_op<Fp<BlsFq>>(op, a, b, out); break;
+  }
+}
+void emu_fp2_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  if (curve == 0) {
+    using F = Fp2<BnFq>; F x, y, r; memcpy(&x, a, sizeof(F)); memcpy(&y, b, sizeof(F));
+    r = op == 0 ? F::mul(x, y) : op == 6 ? F::sqr(x) : op == 3 ? F::inv(x) : F::zero();
+    memcpy(out, &r, sizeof(F));
+  } else {
+    using F = Fp2<BlsFq>; F x, y, r; memcpy(&x, a, sizeof(F)); memcpy(&y, b, sizeof(F));
+    r = op == 0 ? F::mul(x, y) : op == 6 ? F::sqr(x) : op == 3 ? F::inv(x) : F::zero();
+    memcpy(out, &r, sizeof(F));
+  }
+}
+// curve: 0 BN254, 1 BLS12-381; group: 1 or 2
+void emu_pt_op(int curve, int group, int op, const uint32_t* acc, const uint32_t* q, int neg, uint32_t* out) {
+  if (curve == 0 && group == 1) pt_op<Fp<BnFq>>(op, acc, q, neg, out);
+  if (curve == 0 && group == 2) pt_op<Fp2<BnFq>>(op, acc, q, neg, out);
+  if (curve == 1 && group == 1) pt_op<Fp<BlsFq>>(op, acc, q, neg, out);
+  if (curve == 1 && group == 2) pt_op<Fp2<BlsFq>>(op, acc, q, neg, out);
+}
+}

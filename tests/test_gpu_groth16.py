@@ -1,0 +1,149 @@
+"""Groth16 prove path on the GPU vs the oracle (restating groth16/src/prover.rs:124-228 and
+groth16/src/r1cs_to_qap.rs:113-172) on the committed golden instances, including BASELINE
+config 1 (BN256, 2^10-constraint MiMC chain), and through the reference-shaped host API."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from ckb_zkp_b200 import groth16 as zg
+from ckb_zkp_b200.backend import CsrMatrix
+from ckb_zkp_b200.r1cs import ONE
+from oracle.pyref import groth16 as OG
+from oracle.pyref.fields import BLS12_381, BN254, FR, stream_field
+from oracle.pyref.r1cs import ConstraintSystem, mimc_circuit, mini_circuit
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["groth16_mini_bls12_381", "groth16_mini_bn254", "groth16_mimc_bls12_381_2e6", "groth16_mimc_bn254_2e10"]
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def params_from_golden(ctx, g):
+    cid = int(g["curve"])
+    q = lambda k: (g[k + "_xy"], g[k + "_inf"])
+    s1, s2 = g["g1_singles"], g["g2_singles"]
+    return zg.Parameters(ctx, cid, q("a_query"), q("b_g1_query"), q("b_g2_query"), q("h_query"), q("l_query"), s1[0],
+                         s1[1], s1[2], s2[0], s2[1])
+
+
+def matrices(g):
+    return [CsrMatrix(g[w + "_ptr"], g[w + "_col"], g[w + "_val"]) for w in "abc"]
+
+
+def assert_proof(g, proof):
+    for key, got in (("proof_a", proof[0]), ("proof_b", proof[1]), ("proof_c", proof[2])):
+        assert bool(g[key + "_inf"][0]) == got[1], key
+        if not got[1]:
+            assert np.array_equal(g[key + "_xy"][0], got[0]), key
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_witness_map_matches_golden(ctx, name):
+    g = load(name)
+    A, B, C = matrices(g)
+    h = ctx.groth16_h(int(g["curve"]), A, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]))
+    assert np.array_equal(h, g["h"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_prove_matches_golden(ctx, name):
+    g = load(name)
+    params = params_from_golden(ctx, g)
+    A, B, C = matrices(g)
+    proof = ctx.groth16_prove(params.pk, A, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]), g["r"][0], g["s"][0])
+    assert_proof(g, proof)
+    # staged variant (inputs resident in HBM) gives the same bytes, twice in a row
+    ctx.groth16_stage(params.pk, A, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]))
+    for _ in range(2):
+        ctx.groth16_prove_staged(params.pk, g["r"][0], g["s"][0])
+        assert_proof(g, ctx.groth16_fetch_proof(params.pk))
+    params.free()
+
+
+class MiniCircuit:
+    """groth16/tests/mini.rs:12-44"""
+
+    def __init__(self, x, y, z, num):
+        self.x, self.y, self.z, self.num = x, y, z, num
+
+    def generate_constraints(self, cs):
+        vx = cs.alloc(lambda: self.x)
+        vy = cs.alloc(lambda: self.y)
+        vz = cs.alloc_input(lambda: self.z)
+        for _ in range(self.num):
+            cs.enforce([(1, vx)], [(1, vy), (2, ONE)], [(1, vz)])
+
+
+def test_reference_api_mini(ctx):
+    """mirrors groth16/tests/mini.rs:46-97: prove Mini through create_proof / create_random_proof /
+    create_proof_no_zk and compare with the oracle's prover on the same parameters."""
+    g = load("groth16_mini_bls12_381")
+    params = params_from_golden(ctx, g)
+    circuit = MiniCircuit(2, 3, 10, 10)
+    r, s = H.u64_to_int(g["r"][0]), H.u64_to_int(g["s"][0])
+    proof = zg.create_proof(params, circuit, r, s)
+    assert_proof(g, (proof.a, proof.b, proof.c))
+
+    # oracle parameters for fresh r, s (regenerated with the golden file's toxic waste stream)
+    fr = FR[BLS12_381]
+    cs = mini_circuit(ConstraintSystem(fr.p))
+    alpha, beta, gamma, delta, t = [stream_field(1, i, fr.p) for i in range(5)]
+    pk = OG.generate_parameters(cs, BLS12_381, alpha, beta, gamma, delta, t)
+
+    def expect(r, s):
+        a, b, c = OG.create_proof(pk, cs, r, s)
+        return [H.points_array(BLS12_381, grp, [P]) for grp, P in ((1, a), (2, b), (1, c))]
+
+    def check(proof, r, s):
+        for got, (xy, inf) in zip((proof.a, proof.b, proof.c), expect(r, s)):
+            assert got[1] == bool(inf[0])
+            if not got[1]:
+                assert np.array_equal(got[0], xy[0])
+
+    check(zg.create_proof_no_zk(params, circuit), 0, 0)          # r = 0 takes the guard of prover.rs:170
+    rng = random.Random(99)
+    proof = zg.create_random_proof(params, circuit, rng)
+    rng = random.Random(99)
+    r = rng.randrange(fr.p)
+    s = rng.randrange(fr.p)
+    check(proof, r, s)
+    check(zg.create_proof(params, circuit, 0, 12345), 0, 12345)
+    check(zg.create_proof(params, circuit, 777, 0), 777, 0)
+    params.free()
+
+
+def test_unsatisfied_witness_follows_the_pipeline(ctx):
+    """For a witness that does not satisfy the constraints h is not a true quotient; parity then
+    depends on following the literal 7-transform pipeline of r1cs_to_qap.rs:144-169."""
+    cid = BN254
+    fr = FR[cid]
+    cs = ConstraintSystem(fr.p)
+    mimc_circuit(cs, 32)
+    cs.aux_assignment[5] = (cs.aux_assignment[5] + 1) % fr.p
+    assert not cs.is_satisfied()
+    want = OG.witness_map(cs, cid)
+    mats = []
+    for w in "abc":
+        ptr, cols, vals = cs.csr(w)
+        mats.append(CsrMatrix(np.asarray(ptr, dtype=np.uint32), np.asarray(cols, dtype=np.uint32), H.fr_array(cid, vals)))
+    h = ctx.groth16_h(cid, mats[0], mats[1], mats[2], H.fr_array(cid, cs.full_assignment()), cs.num_inputs, cs.num_aux)
+    assert H.fr_ints(cid, h, mont=False) == want
+    assert want[-1] != 0          # a satisfied witness would give h[N-1] == 0
+
+
+def test_error_behaviour(ctx):
+    from ckb_zkp_b200.backend import ZkbError
+    g = load("groth16_mini_bn254")
+    A, B, C = matrices(g)
+    # row counts differ
+    bad = CsrMatrix(g["a_ptr"][:-1], g["a_col"][:int(g["a_ptr"][-2])], g["a_val"][:int(g["a_ptr"][-2])])
+    with pytest.raises(ZkbError):
+        ctx.groth16_h(BN254, bad, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]))
+    with pytest.raises(ValueError):
+        ctx.groth16_h(BN254, A, B, C, g["z"][:-1], int(g["n_inputs"]), int(g["n_aux"]))
