@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""Headline benchmark: Groth16 proofs/sec, BLS12-381, 2^20-constraint synthetic R1CS (BASELINE.json
+configs[1]) on N B200s, one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--log-constraints L]
+
+A step = one pass of the prove path (groth16/src/prover.rs:148-210: witness_map, into_repr, five
+MSMs, proof assembly) over one R1CS instance + assignment.
+  value  proofs/s with matrices, assignment and proving key resident in HBM (zkb_groth16_prove_staged),
+         timed with CUDA events on the library's stream, max over ranks, whole job (N ranks prove N
+         independent witnesses per step: weak scaling, no data-path collective).
+  e2e    the same through the reference-facing call with HOST buffers (zkb_groth16_prove): H2D of the
+         matrices and the assignment from pinned memory and D2H of the proof inside the timed region.
+  roofline      bucket-accumulation kernel (k_accumulate): algorithmic MSM bytes / measured duration.
+  cpu_baseline  the C++ restatement of the reference's CPU prover (oracle/c, arkworks-0.2 algorithms)
+                timed on this box's host cores on a bounded sample.
+`--impl reference` times that CPU restatement alone (the Rust reference cannot be built: no toolchain,
+arkworks un-vendored) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "groth16_proofs_per_sec_bls12_381_2e20_constraints"
+UNIT = "proofs/s"
+CURVE = 1   # BLS12-381
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-constraints", type=int, default=20)
+    ap.add_argument("--cpu-sample-log", type=int, default=15, help="log2 constraints of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.samples.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def start(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=10)
+        sm = sorted(int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.startswith("Active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work of one proof
+# ------------------------------------------------------------------------------------------------
+def ark_window(n):
+    l = (n - 1).bit_length() if n > 1 else 0
+    return 3 if n < 32 else l * 69 // 100 + 2
+
+
+def proof_work(n_constraints):
+    """MSM pair counts, algorithmic bytes and the reference algorithm's group additions per proof."""
+    n_inputs, n_aux = 2, n_constraints + 1
+    n_vars = n_inputs + n_aux
+    N = 1 << (n_constraints + n_inputs - 1).bit_length()
+    msm = {"a": n_vars - 1, "b_g1": n_vars - 1, "b_g2": n_vars - 1, "l": n_aux, "h": N - 1}
+    g1 = 32 + 96
+    g2 = 32 + 192
+    msm_bytes = sum(v * (g2 if k == "b_g2" else g1) for k, v in msm.items())
+    nnz = 5 * n_constraints
+    bytes_total = 7 * 2 * N * 32 + nnz * 40 + 3 * N * 32 + msm_bytes
+
+    def adds(n):
+        c = ark_window(n)
+        w = -(-255 // c)
+        return n * w + 2 * ((1 << c) - 1) * w
+    return {"msm_pairs": msm, "msm_bytes": msm_bytes, "bytes": bytes_total, "domain": N,
+            "ref_group_adds": sum(adds(v) * (3 if k == "b_g2" else 1) for k, v in msm.items())}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (oracle/c: restated arkworks-0.2 prover) -- the only place oracle/ is touched
+# ------------------------------------------------------------------------------------------------
+def cpu_prove_setup(log_n):
+    """instance + key for the CPU sample, built without the GPU (oracle fixed-base multiplication)"""
+    from ckb_zkp_b200 import synth
+    from oracle import cref
+    n = 1 << log_n
+    inst = synth.MimcInstance(CURVE, n)
+    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, proof_work(n)["domain"],
+                             b_zero_cols=np.arange(4, 4 + n, 2))
+    to_mont = lambda ints: cref.fr_convert(CURVE, synth.ints_to_limbs(ints), True)
+    rounds = n // 2
+    consts = synth.stream_field_ints(synth.MIMC_SEED, 2, rounds, inst.p)
+    table = to_mont(consts + [1, inst.p - 1])
+    mats = []
+    for which in "ABC":
+        row_ptr, cols, codes, per = getattr(inst, which)
+        idx = np.where(codes == 1, rounds, np.where(codes == -2, rounds + 1, np.arange(len(codes)) // per))
+        mats.append((row_ptr, cols, np.ascontiguousarray(table[idx])))
+    z = to_mont(inst.z)
+    g1, g2 = synth.generator_mont(CURVE, 1), synth.generator_mont(CURVE, 2)
+    pts = lambda grp, k: cref.fixed_base_mul(CURVE, grp, g1 if grp == 1 else g2, k)
+    pk = {"a": pts(1, key.a), "b1": pts(1, key.b), "b2": pts(2, key.b), "h": pts(1, key.h), "l": pts(1, key.l),
+          "g1_singles": pts(1, np.stack([key.alpha, key.beta, key.delta]))[0],
+          "g2_singles": pts(2, np.stack([key.beta, key.delta]))[0]}
+    return inst, key, mats, z, pk
+
+
+def cpu_prove_time(log_n, steps, warmup, full_log):
+    """seconds per CPU proof at 2^log_n constraints, and that time scaled to 2^full_log constraints by
+    the ratio of the reference algorithm's own group-addition counts (MSM dominates; the window size
+    grows with n, so the scale factor is a little below the ratio of sizes)."""
+    from oracle import cref
+    inst, key, mats, z, pk = cpu_prove_setup(log_n)
+    r = np.array([5, 0, 0, 0], dtype=np.uint64)
+    s = np.array([7, 0, 0, 0], dtype=np.uint64)
+    threads = cref.threads()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        cref.groth16_prove(CURVE, pk, mats[0], mats[1], mats[2], z, inst.n_inputs, inst.n_aux, r, s, threads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    scale = proof_work(1 << full_log)["ref_group_adds"] / proof_work(1 << log_n)["ref_group_adds"]
+    return t, t * scale, threads, scale
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    t0 = time.perf_counter()
+    t_sample, t_full, threads, scale = cpu_prove_time(args.cpu_sample_log, steps, min(warmup, 1), args.log_constraints)
+    value = 1.0 / t_full
+    sample = ("full Groth16 prove (witness_map + 5 MSMs + assembly) at 2^%d constraints, %.3f s/proof, scaled x%.2f "
+              "to 2^%d by the reference algorithm's group-addition count" % (args.cpu_sample_log, t_sample, scale,
+                                                                             args.log_constraints))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (modular integer arithmetic, 255-bit Fr / 381-bit Fq)", "data": "synthetic",
+            "config": {"workload": "Groth16 prove, BLS12-381, 2^%d-constraint MiMC-chain R1CS" % args.log_constraints,
+                       "note": "restated reference CPU path (arkworks-0.2 algorithms, oracle/c/zkref.cpp); the Rust "
+                               "reference itself cannot be built in this image"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from ckb_zkp_b200 import synth
+    from ckb_zkp_b200.backend import Context
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    ctx = Context(local)      # raises if libzkb.so or the B200 is missing: no fallback
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = 1 << args.log_constraints
+    work = proof_work(n)
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+
+    # ---- workload: every rank proves its own witness (different MiMC seed per rank) of the same circuit shape
+    t_setup = time.perf_counter()
+    inst = synth.MimcInstance(CURVE, n, seed=synth.MIMC_SEED + rank)
+    A, B, C, z_mont = inst.device_form(ctx)
+    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, work["domain"], b_zero_cols=np.arange(4, 4 + n, 2))
+    params = key.upload(ctx, CURVE)
+    # pinned host copies for the end-to-end path
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    from ckb_zkp_b200.backend import CsrMatrix
+    Ap, Bp, Cp = [CsrMatrix(pin(m.row_ptr), pin(m.col_idx), pin(m.coeff)) for m in (A, B, C)]
+    zp = pin(z_mont)
+    r = synth.ints_to_limbs([0x1234567 + rank])[0]
+    s = synth.ints_to_limbs([0x89ABCDE + rank])[0]
+    setup_s = time.perf_counter() - t_setup
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # ---- device-resident timing
+    ctx.groth16_stage(params.pk, Ap, Bp, Cp, zp, inst.n_inputs, inst.n_aux)
+    for _ in range(warmup):
+        ctx.groth16_prove_staged(params.pk, r, s)
+    ctx.sync()
+    proof = ctx.groth16_fetch_proof(params.pk)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    launches0 = ctx.launch_count
+    prof = hasattr(ctx, "prof_enable")
+    if prof:
+        ctx.prof_enable(True)
+    for i in range(steps):
+        flush.fill_(i & 0xFF)             # evict L2 between timed iterations (working set also exceeds L2)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            starts[i].record()
+            ctx.groth16_prove_staged(params.pk, r, s)
+            ends[i].record()
+    barrier()
+    launches = ctx.launch_count - launches0
+    prof_out = ctx.prof_read() if prof else None
+    if prof:
+        ctx.prof_enable(False)
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(starts, ends))
+    assert ctx.groth16_fetch_proof(params.pk)[0][0].tolist() == proof[0][0].tolist()
+
+    # ---- end to end through the host-buffer call
+    for _ in range(2):
+        ctx.groth16_prove(params.pk, Ap, Bp, Cp, zp, inst.n_inputs, inst.n_aux, r, s)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        proof_e2e = ctx.groth16_prove(params.pk, Ap, Bp, Cp, zp, inst.n_inputs, inst.n_aux, r, s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    assert proof_e2e[2][0].tolist() == proof[2][0].tolist()
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = t.tolist()
+
+    # ---- full-size correctness: every proof element is a known multiple of the generator
+    verified = None
+    if not args.no_verify and rank == 0:
+        verified = verify_in_exponent(ctx, inst, key, A, B, C, z_mont, r, s, proof)
+
+    h2d = zp.nbytes + sum(m.row_ptr.nbytes + m.col_idx.nbytes + m.coeff.nbytes for m in (Ap, Bp, Cp))
+    d2h = 2 * 96 + 192 + 16
+
+    line = None
+    if rank == 0:
+        value = world * steps / (dev_ms_max / 1e3)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u32 limbs (modular integer arithmetic, 255-bit Fr / 381-bit Fq)", "data": "synthetic",
+                "config": {"workload": "Groth16 prove, BLS12-381, 2^%d-constraint MiMC-chain R1CS, 1 proof per GPU per "
+                                       "step (BASELINE configs[1])" % args.log_constraints,
+                           "domain": work["domain"], "msm_pairs": work["msm_pairs"],
+                           "algorithmic_bytes_per_proof": work["bytes"], "l2": "flushed between timed iterations",
+                           "parallelism": "independent proofs per rank, no collective"},
+                "e2e": {"value": world * steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clocks, "verified_in_exponent": verified, "setup_s": round(setup_s, 1)}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        if prof_out and prof_out["launches"]:
+            ms = prof_out["ms"] / prof_out["launches"]
+            bytes_per = prof_out["alg_bytes"] / prof_out["launches"]
+            ach = bytes_per / (ms * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "k_accumulate (Pippenger bucket accumulation)", "achieved": ach,
+                                "peak": peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                                "unit": "GB/s", "frac": ach / peak, "traffic": None, "avg_launch_ms": ms,
+                                "launches": prof_out["launches"], "share_of_step": prof_out["ms"] / dev_ms_max,
+                                "note": "MSM is integer-ALU bound: see DESIGN.md for the IMAD roofline"}
+        else:
+            ach = work["bytes"] / (dev_ms_max / steps * 1e-3) / 1e9
+            line["roofline"] = {"bound": "hbm", "kernel": "whole prove step", "achieved": ach, "peak": peak, "unit": "GB/s",
+                                "frac": ach / peak, "traffic": None}
+    params.free()
+    ctx.close()
+    del flush
+    torch.cuda.empty_cache()
+
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            t_sample, t_full, threads, scale = cpu_prove_time(args.cpu_sample_log, 2, 1, args.log_constraints)
+            line["cpu_baseline"] = {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "full Groth16 prove at 2^%d constraints (%.3f s), scaled x%.2f to 2^%d by the "
+                                              "reference algorithm's group-addition count; restated arkworks-0.2 CPU "
+                                              "prover (oracle/c)" % (args.cpu_sample_log, t_sample, scale,
+                                                                     args.log_constraints)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def verify_in_exponent(ctx, inst, key, A, B, C, z_mont, r, s, proof):
+    """proof == (A_exp * G1, B_exp * G2, C_exp * G1) with exponents evaluated in Fr from the key's known
+    exponents, the assignment and the GPU's own h (h itself is checked against the oracle in tests/)."""
+    from ckb_zkp_b200 import synth
+    p = inst.p
+    h = synth.limbs_to_ints(ctx.groth16_h(inst.curve, A, B, C, z_mont, inst.n_inputs, inst.n_aux))
+    ea, eb, ec = key.expected_exponents(p, inst.z, h, synth.limbs_to_ints(r.reshape(1, 4))[0],
+                                        synth.limbs_to_ints(s.reshape(1, 4))[0])
+    ok = True
+    for grp, e, got in ((1, ea, proof[0]), (2, eb, proof[1]), (1, ec, proof[2])):
+        xy, inf = ctx.fixed_base_mul(inst.curve, grp, synth.generator_mont(inst.curve, grp), synth.ints_to_limbs([e]))
+        ok = ok and bool(inf[0]) == got[1] and (got[1] or np.array_equal(xy[0], got[0]))
+    return bool(ok)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -120,6 +120,15 @@ class Context:
     def launch_count(self):
         return int(self.lib.zkb_launch_count(self.handle))
 
+    def prof_enable(self, on):
+        self._check(self.lib.zkb_prof_enable(self.handle, 1 if on else 0))
+
+    def prof_read(self):
+        """{'ms', 'launches', 'alg_bytes'} of the bucket-accumulation kernel since prof_enable(True)"""
+        ms, n, b = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
+        self._check(self.lib.zkb_prof_read(self.handle, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(b)))
+        return {"ms": ms.value, "launches": int(n.value), "alg_bytes": b.value}
+
     # -- SRS / MSM ----------------------------------------------------------------------------
     def srs_upload(self, curve, group, xy, inf=None, precompute=True):
         xy = np.ascontiguousarray(xy, dtype=np.uint64)

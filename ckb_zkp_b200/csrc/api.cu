@@ -95,6 +95,7 @@ void zkb_destroy(zkb_ctx* ctx) {
   groth16_free_stage(ctx);
   ntt_free_domains(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   for (int i = 0; i < kNumSideStreams; i++) {
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
@@ -113,6 +114,32 @@ int zkb_sync(zkb_ctx* ctx) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+  return ZKB_OK;
+}
+
+// ---- kernel timing (bench.py's roofline figure) ------------------------------------------------
+int zkb_prof_enable(zkb_ctx* ctx, int on) {
+  if (!ctx) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->prof_on = on != 0;
+  ctx->prof_used = 0;
+  ctx->prof_alg_bytes = 0;
+  return ZKB_OK;
+}
+int zkb_prof_read(zkb_ctx* ctx, double* ms_total, uint64_t* launches, double* alg_bytes_total) {
+  if (!ctx || !ms_total || !launches || !alg_bytes_total) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  ZKB_CUDA(ctx, cudaDeviceSynchronize());
+  double ms = 0;
+  for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+    float t = 0;
+    ZKB_CUDA(ctx, cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    ms += t;
+  }
+  *ms_total = ms;
+  *launches = ctx->prof_used / 2;
+  *alg_bytes_total = ctx->prof_alg_bytes;
   return ZKB_OK;
 }
 

@@ -38,6 +38,11 @@ struct zkb_ctx {
   // pinned bounce buffer for small results
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // optional timing of the dominant kernel (bucket accumulation) with CUDA events on its stream
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;   // start/stop pairs
+  size_t prof_used = 0;
+  double prof_alg_bytes = 0;
 };
 
 namespace zkb {
@@ -99,6 +104,25 @@ struct Scratch {
     return ZKB_OK;
   }
 };
+
+// bracket one launch of the profiled kernel; alg_bytes = algorithmic bytes that launch streams
+inline void prof_begin(zkb_ctx* ctx, cudaStream_t st) {
+  if (!ctx->prof_on) return;
+  if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+    for (int i = 0; i < 2; i++) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { ctx->prof_on = false; return; }
+      ctx->prof_events.push_back(e);
+    }
+  }
+  cudaEventRecord(ctx->prof_events[ctx->prof_used], st);
+}
+inline void prof_end(zkb_ctx* ctx, cudaStream_t st, double alg_bytes) {
+  if (!ctx->prof_on) return;
+  cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st);
+  ctx->prof_used += 2;
+  ctx->prof_alg_bytes += alg_bytes;
+}
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 inline unsigned ceil_log2(size_t n) {

@@ -21,6 +21,16 @@ struct Affine {
   ZKB_HD static Affine inf() { return {F::zero(), F::zero()}; }
 };
 
+// Out-of-line (never inlined) versions of the group operations, defined after XYZZ.  Cold kernels
+// and the rare branches of the hot ones call these so that every translation unit carries each
+// unrolled formula once instead of once per call site (ptxas time and instruction-cache footprint).
+template <class F> struct XYZZ;
+template <class F> ZKB_NOINLINE void pt_add(XYZZ<F>& a, const XYZZ<F>& b);
+template <class F> ZKB_NOINLINE void pt_dbl(XYZZ<F>& a);
+template <class F> ZKB_NOINLINE void pt_dbl_affine(XYZZ<F>& out, const F& x, const F& y);
+template <class F> ZKB_NOINLINE void pt_madd(XYZZ<F>& a, const Affine<F>& p, bool negate);
+template <class F> ZKB_NOINLINE void pt_to_affine(Affine<F>& out, const XYZZ<F>& a);
+
 template <class F>
 struct XYZZ {
   F X, Y, ZZ, ZZZ;
@@ -76,7 +86,7 @@ struct XYZZ {
     F Pp = F::sub(U2, X);
     F R = F::sub(S2, Y);
     if (Pp.is_zero()) {
-      if (R.is_zero()) *this = dbl_affine(x2, y2);
+      if (R.is_zero()) pt_dbl_affine(*this, x2, y2);
       else *this = inf();
       return;
     }
@@ -105,7 +115,7 @@ struct XYZZ {
     F Pp = F::sub(U2, U1);
     F R = F::sub(S2, S1);
     if (Pp.is_zero()) {
-      if (R.is_zero()) *this = dbl(*this);
+      if (R.is_zero()) pt_dbl(*this);
       else *this = inf();
       return;
     }
@@ -136,13 +146,19 @@ struct XYZZ {
     bool started = false;
     for (int i = nlimbs - 1; i >= 0; i--) {
       for (int b = 31; b >= 0; b--) {
-        if (started) r = dbl(r);
-        if ((k[i] >> b) & 1) { r.add(p); started = true; }
+        if (started) pt_dbl(r);
+        if ((k[i] >> b) & 1) { pt_add(r, p); started = true; }
       }
     }
     return r;
   }
   ZKB_HD static XYZZ mul_u32(const XYZZ& p, uint32_t k) { return mul_limbs(p, &k, 1); }
 };
+
+template <class F> ZKB_NOINLINE void pt_add(XYZZ<F>& a, const XYZZ<F>& b) { a.add(b); }
+template <class F> ZKB_NOINLINE void pt_dbl(XYZZ<F>& a) { a = XYZZ<F>::dbl(a); }
+template <class F> ZKB_NOINLINE void pt_dbl_affine(XYZZ<F>& out, const F& x, const F& y) { out = XYZZ<F>::dbl_affine(x, y); }
+template <class F> ZKB_NOINLINE void pt_madd(XYZZ<F>& a, const Affine<F>& p, bool negate) { a.madd(p, negate); }
+template <class F> ZKB_NOINLINE void pt_to_affine(Affine<F>& out, const XYZZ<F>& a) { out = a.to_affine(); }
 
 }  // namespace zkb

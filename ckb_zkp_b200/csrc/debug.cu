@@ -36,15 +36,16 @@ __global__ void k_dbg_pt(int op, const XYZZ<F>* acc, const uint32_t* q, int q_wo
   const uint32_t* qi = q + (size_t)i * q_words;
   uint32_t* oi = out + (size_t)i * out_words;
   if (op == 0) {
-    a.madd(*reinterpret_cast<const Affine<F>*>(qi), neg != 0);
+    pt_madd(a, *reinterpret_cast<const Affine<F>*>(qi), neg != 0);
     *reinterpret_cast<XYZZ<F>*>(oi) = a;
   } else if (op == 1) {
-    a.add(*reinterpret_cast<const XYZZ<F>*>(qi));
+    pt_add(a, *reinterpret_cast<const XYZZ<F>*>(qi));
     *reinterpret_cast<XYZZ<F>*>(oi) = a;
   } else if (op == 2) {
-    *reinterpret_cast<XYZZ<F>*>(oi) = XYZZ<F>::dbl(a);
+    pt_dbl(a);
+    *reinterpret_cast<XYZZ<F>*>(oi) = a;
   } else if (op == 3) {
-    *reinterpret_cast<Affine<F>*>(oi) = a.to_affine();
+    pt_to_affine(*reinterpret_cast<Affine<F>*>(oi), a);
   } else if (op == 4) {
     uint32_t k[8];
     for (int j = 0; j < 8; j++) k[j] = qi[j];

@@ -110,9 +110,9 @@ __global__ void k_g16_coeffs(const Fp<FrP>* scal, const Affine<Fq>* a0, const Af
   Fr r = scal[0], s = scal[1];
   if (blockIdx.x == 0) {
     XYZZ<Fq> g = ld_vec_rw(&res->r_delta);
-    g.madd(*a0);
-    g.add(ld_vec_rw(&res->msm_a));
-    g.madd(g1_singles[0]);               // alpha_g1
+    pt_madd(g, *a0, false);
+    { XYZZ<Fq> m = ld_vec_rw(&res->msm_a); pt_add(g, m); }
+    pt_madd(g, g1_singles[0], false);    // alpha_g1
     st_vec(&res->g_a, g);
     st_vec(&res->s_g_a, XYZZ<Fq>::mul_limbs(g, s.v, Fr::N));
   }
@@ -120,18 +120,18 @@ __global__ void k_g16_coeffs(const Fp<FrP>* scal, const Affine<Fq>* a0, const Af
     XYZZ<Fq> g = XYZZ<Fq>::inf();
     if (!r.is_zero()) {                  // the guard is on r (prover.rs:170)
       g = ld_vec_rw(&res->s_delta);
-      g.madd(*b1_0);
-      g.add(ld_vec_rw(&res->msm_b1));
-      g.madd(g1_singles[1]);             // beta_g1
+      pt_madd(g, *b1_0, false);
+      { XYZZ<Fq> m = ld_vec_rw(&res->msm_b1); pt_add(g, m); }
+      pt_madd(g, g1_singles[1], false);  // beta_g1
     }
     st_vec(&res->g1_b, g);
     st_vec(&res->r_g1_b, XYZZ<Fq>::mul_limbs(g, r.v, Fr::N));
   }
   if (blockIdx.x == 2) {
     XYZZ<Fq2> g = ld_vec_rw(&res->s_delta2);
-    g.madd(*b2_0);
-    g.add(ld_vec_rw(&res->msm_b2));
-    g.madd(g2_singles[0]);               // beta_g2
+    pt_madd(g, *b2_0, false);
+    { XYZZ<Fq2> m = ld_vec_rw(&res->msm_b2); pt_add(g, m); }
+    pt_madd(g, g2_singles[0], false);    // beta_g2
     st_vec(&res->g2_b, g);
   }
 }
@@ -142,23 +142,32 @@ __global__ void k_g16_finish(G16Results<Fq, Fq2>* res) {
   if (threadIdx.x) return;
   if (blockIdx.x == 0) {
     XYZZ<Fq> g = ld_vec_rw(&res->g_a);
-    st_vec(&res->proof_a, g.to_affine());
+    Affine<Fq> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_a, a);
     res->inf[0] = g.is_inf();
   }
   if (blockIdx.x == 1) {
     XYZZ<Fq2> g = ld_vec_rw(&res->g2_b);
-    st_vec(&res->proof_b, g.to_affine());
+    Affine<Fq2> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_b, a);
     res->inf[1] = g.is_inf();
   }
   if (blockIdx.x == 2) {
     XYZZ<Fq> g = ld_vec_rw(&res->s_g_a);
-    g.add(ld_vec_rw(&res->r_g1_b));
-    XYZZ<Fq> d = ld_vec_rw(&res->rs_delta);
-    d.neg_in_place();
-    g.add(d);
-    g.add(ld_vec_rw(&res->msm_l));
-    g.add(ld_vec_rw(&res->msm_h));
-    st_vec(&res->proof_c, g.to_affine());
+    XYZZ<Fq> t = ld_vec_rw(&res->r_g1_b);
+    pt_add(g, t);
+    t = ld_vec_rw(&res->rs_delta);
+    t.neg_in_place();
+    pt_add(g, t);
+    t = ld_vec_rw(&res->msm_l);
+    pt_add(g, t);
+    t = ld_vec_rw(&res->msm_h);
+    pt_add(g, t);
+    Affine<Fq> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_c, a);
     res->inf[2] = g.is_inf();
   }
 }

@@ -18,7 +18,8 @@ k_fixed_base_mul(const Affine<F>* __restrict__ base, const uint32_t* __restrict_
 #pragma unroll
   for (int j = 0; j < kScalarLimbs; j++) k[j] = scalars[(size_t)i * kScalarLimbs + j];
   XYZZ<F> r = XYZZ<F>::mul_limbs(p, k, kScalarLimbs);
-  Affine<F> a = r.to_affine();
+  Affine<F> a;
+  pt_to_affine(a, r);
   st_vec(&out_xy[i], a);
   out_inf[i] = r.is_inf() ? 1 : 0;
 }

@@ -221,17 +221,17 @@ k_fold(const XYZZ<F>* __restrict__ in_pts, const int32_t* __restrict__ in_keys, 
     if (k != cur) {
       if (cur >= 0) {
         if (is_cont) { st_vec(&out_pts[u], acc); out_keys[u] = cur; wrote_cont = true; }
-        else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); t.add(acc); st_vec(&bucket_acc[cur], t); }
+        else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); pt_add(t, acc); st_vec(&bucket_acc[cur], t); }
       }
       cur = k;
       acc = XYZZ<F>::inf();
       is_cont = (i == start) && start > 0 && k >= 0 && in_keys[start - 1] == k;
     }
-    if (k >= 0) acc.add(ld_vec_rw(&in_pts[i]));
+    if (k >= 0) { XYZZ<F> q = ld_vec_rw(&in_pts[i]); pt_add(acc, q); }
   }
   if (cur >= 0) {
     if (is_cont) { st_vec(&out_pts[u], acc); out_keys[u] = cur; wrote_cont = true; }
-    else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); t.add(acc); st_vec(&bucket_acc[cur], t); }
+    else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); pt_add(t, acc); st_vec(&bucket_acc[cur], t); }
   }
   if (!wrote_cont) out_keys[u] = -1;
 }
@@ -251,10 +251,11 @@ k_bucket_reduce(const XYZZ<F>* __restrict__ bucket_acc, uint32_t B, uint32_t n_s
   const XYZZ<F>* src = bucket_acc + (size_t)set * B;
   XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
   for (uint32_t b = b1; b-- > b0;) {
-    running.add(ld_vec_rw(&src[b]));
-    acc.add(running);
+    XYZZ<F> q = ld_vec_rw(&src[b]);
+    pt_add(running, q);
+    pt_add(acc, running);
   }
-  if (b0 && !running.is_inf()) acc.add(XYZZ<F>::mul_u32(running, b0));
+  if (b0 && !running.is_inf()) { XYZZ<F> m = XYZZ<F>::mul_u32(running, b0); pt_add(acc, m); }
   st_vec(&out[u], acc);
 }
 
@@ -267,13 +268,13 @@ k_sum_points(const XYZZ<F>* __restrict__ in, uint32_t n_per_set, XYZZ<F>* __rest
   const XYZZ<F>* src = in + (size_t)set * n_per_set;
   uint32_t first = (blockIdx.x * blockDim.x + threadIdx.x) * per_thread;
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t i = first; i < first + per_thread && i < n_per_set; i++) acc.add(ld_vec_rw(&src[i]));
+  for (uint32_t i = first; i < first + per_thread && i < n_per_set; i++) { XYZZ<F> q = ld_vec_rw(&src[i]); pt_add(acc, q); }
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int s = 32; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) {
-      XYZZ<F> a = sh[threadIdx.x];
-      a.add(sh[threadIdx.x + s]);
+      XYZZ<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+      pt_add(a, b);
       sh[threadIdx.x] = a;
     }
     __syncthreads();
@@ -287,8 +288,9 @@ __global__ void k_window_combine(const XYZZ<F>* __restrict__ sums, uint32_t n_se
   if (threadIdx.x | blockIdx.x) return;
   XYZZ<F> total = ld_vec_rw(&sums[n_sets - 1]);
   for (int j = (int)n_sets - 2; j >= 0; j--) {
-    for (int k = 0; k < c; k++) total = XYZZ<F>::dbl(total);
-    total.add(ld_vec_rw(&sums[j]));
+    for (int k = 0; k < c; k++) pt_dbl(total);
+    XYZZ<F> q = ld_vec_rw(&sums[j]);
+    pt_add(total, q);
   }
   st_vec(out, total);
 }
@@ -299,7 +301,8 @@ __global__ void k_to_affine(const XYZZ<F>* __restrict__ in, uint32_t n, Affine<F
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   XYZZ<F> p = ld_vec_rw(&in[i]);
-  Affine<F> a = p.to_affine();
+  Affine<F> a;
+  pt_to_affine(a, p);
   st_vec(&out_xy[i], a);
   out_inf[i] = p.is_inf() ? 1 : 0;
 }
@@ -320,8 +323,9 @@ k_precompute(Affine<F>* table, uint32_t n, int c, int W) {
   Affine<F> p = ld_vec_rw(&table[i]);
   XYZZ<F> q = XYZZ<F>::from_affine(p);
   for (int j = 1; j < W; j++) {
-    for (int k = 0; k < c; k++) q = XYZZ<F>::dbl(q);
-    Affine<F> a = q.to_affine();
+    for (int k = 0; k < c; k++) pt_dbl(q);
+    Affine<F> a;
+    pt_to_affine(a, q);
     st_vec(&table[(size_t)j * n + i], a);
     q = XYZZ<F>::from_affine(a);       // keep Z = 1 so the next inversion input stays small
   }
@@ -416,8 +420,10 @@ struct MsmEngine {
     ZKB_TRY(ws.alloc(&cont_b, n_fold1));
     ZKB_TRY(ws.alloc(&key_b, n_fold1));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));
+    prof_begin(ctx, st);
     ZKB_LAUNCH(ctx, (k_accumulate<F>), ceil_div(n_acc_threads, 128), 128, 0, st, entries, offsets, n_buckets,
                (const Aff*)srs->table, bucket_acc, cont_a, key_a, n_acc_threads);
+    prof_end(ctx, st, (double)n * (32.0 + sizeof(Aff)));   // one read of each (scalar, base) pair
     {
       uint32_t n_in = n_acc_threads;
       Pt *pin = cont_a, *pout = cont_b;

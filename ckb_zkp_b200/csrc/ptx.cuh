@@ -9,9 +9,11 @@
 #ifdef __CUDACC__
 #define ZKB_HD __host__ __device__ __forceinline__
 #define ZKB_D __device__ __forceinline__
+#define ZKB_NOINLINE __host__ __device__ __noinline__
 #else
 #define ZKB_HD inline
 #define ZKB_D inline
+#define ZKB_NOINLINE inline
 #endif
 
 namespace zkb {

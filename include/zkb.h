@@ -73,6 +73,12 @@ int zkb_sync(zkb_ctx* ctx);
 /* number of kernels this ctx has launched so far (bench.py's `gpu_launches`). */
 uint64_t zkb_launch_count(zkb_ctx* ctx);
 
+/* CUDA-event timing of the dominant kernel (MSM bucket accumulation) on its launch stream:
+ * enable resets the counters; read synchronises and returns the summed duration, the number of
+ * launches and the algorithmic bytes (n * (32 + sizeof affine base) per MSM) they covered. */
+int zkb_prof_enable(zkb_ctx* ctx, int on);
+int zkb_prof_read(zkb_ctx* ctx, double* ms_total, uint64_t* launches, double* alg_bytes_total);
+
 /* ---- bases resident in HBM --------------------------------------------------------------
  * Replaces the `&[G::Affine]` argument of ark_ec::msm::VariableBaseMSM::multi_scalar_mul
  * (call sites groth16/src/prover.rs:187,190,220; marlin/src/pc/kzg10.rs:109,118,137,146;
