@@ -299,19 +299,27 @@ struct Groth16Impl {
     Fr r_val, s_val;      // by-value kernel arguments: no staging buffer to race on
     memcpy(r_val.v, r, 32);
     memcpy(s_val.v, sc, 32);
-    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, st, r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
+    // the four delta multiples are independent of everything else: side stream, joined before the assembly
+    ZKB_TRY(fork_streams(ctx, 1));
+    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, ctx->side[0], r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
                (const Affine<Fq2>*)pk->g2_singles, res);
     // assignment = into_repr(input[1..] ++ aux)  (prover.rs:150-158)
     const size_t n_assign = s->n_inputs - 1 + s->n_aux;
     ZKB_TRY(fr_convert_dev(ctx, st, CURVE, (const Fr*)s->z.p + 1, s->z_repr.p, n_assign, 0));
     const uint32_t* zr = (const uint32_t*)s->z_repr.p;
     auto clamp = [](size_t n, const zkb_srs* srs, size_t off) { size_t a = srs->n > off ? srs->n - off : 0; return n < a ? n : a; };
-    ZKB_TRY(g1->msm_run(ctx, st, pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
-    ZKB_TRY(g1->msm_run(ctx, st, pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
-    ZKB_TRY(g2->msm_run(ctx, st, pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
-    ZKB_TRY(g1->msm_run(ctx, st, pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    // The four MSMs over the assignment are independent of each other and of witness_map: one
+    // side stream each, so the low-parallelism tails of one (bucket reduction, final sums) overlap
+    // the bucket accumulation of another; witness_map and the H MSM stay on the main stream.
+    ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (int i = 1; i <= 4; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    ZKB_TRY(g2->msm_run(ctx, ctx->side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
+    ZKB_TRY(g1->msm_run(ctx, ctx->side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
+    ZKB_TRY(g1->msm_run(ctx, ctx->side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    ZKB_TRY(g1->msm_run(ctx, ctx->side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
     ZKB_TRY(compute_h(ctx, st));
     ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
+    ZKB_TRY(join_streams(ctx, 5));
     ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, st, (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
                (const Affine<Fq>*)pk->b_g1->table, (const Affine<Fq2>*)pk->b_g2->table,
                (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles, res);

@@ -7,15 +7,15 @@
 //
 //   * signed c-bit digits (half the buckets of the reference's unsigned windows);
 //   * with ZKB_SRS_PRECOMPUTE the bases 2^(c*j) * P_i of every window j are resident in
-//     HBM (180 GB makes a 16x copy of the SRS cheap), so ALL windows share ONE bucket
+//     HBM (180 GB makes a 13x copy of the SRS cheap), so ALL windows share ONE bucket
 //     array: no per-window reduction and no doubling chain at the end;
 //   * counting sort of (bucket, base index) pairs: histogram -> exclusive scan -> scatter;
-//   * bucket accumulation is chunked over the SORTED list -- every thread adds exactly K
-//     consecutive entries whatever the bucket sizes are (boolean-heavy witnesses put
-//     millions of entries into one bucket: a thread-per-bucket schedule would serialise);
-//     the first partial bucket of a chunk is a "continuation", folded in log_K2 levels;
-//   * bucket reduction sum (b+1) * S_b by per-thread running sums over M buckets plus a
-//     short scalar multiplication by the chunk offset, then a tree sum.
+//   * bucket accumulation: one thread per bucket, buckets ordered by decreasing size so the
+//     32 lanes of a warp run the same trip count; buckets above kBigBucket entries
+//     (boolean-heavy witnesses put a large share of all entries into the "digit = 1" bucket)
+//     are cut into 2048-entry chunks, one block each, and folded by a second block-level pass;
+//   * bucket reduction sum_b (b + 1) * S_b through the row / column sums of the bucket array
+//     viewed as a matrix [hi][lo]:  sum_hi (hi * L) * R_hi + sum_lo (lo + 1) * C_lo.
 //
 // Entry layout (uint32): bit 31 = negate, bits 0..30 = index into the base table.
 #pragma once
@@ -35,9 +35,11 @@ struct zkb_srs {
 
 namespace zkb {
 
-constexpr int kAccK = 16;     // sorted entries per accumulate thread
-constexpr int kFoldK = 16;    // continuation points per fold thread
-constexpr int kRedM = 16;     // buckets per reduce thread
+constexpr int kBigBucket = 256;         // buckets with more entries take the chunked path
+constexpr int kChunkThreads = 128;      // threads per big-bucket chunk block
+constexpr int kChunkPer = 16;           // entries per thread in a chunk
+constexpr int kChunk = kChunkThreads * kChunkPer;
+constexpr int kSegK = 8;                // points summed per thread in the row / column passes
 constexpr int kScalarLimbs = 8;
 
 // ------------------------------------------------------------------------------------------
@@ -162,101 +164,198 @@ static __global__ void k_scan_finish(uint32_t* offsets, uint32_t n, const uint32
 }
 
 // ------------------------------------------------------------------------------------------
-// bucket accumulation over the sorted entry list, K entries per thread
+// bucket scheduling: order the regular buckets by decreasing size, list the big ones
 // ------------------------------------------------------------------------------------------
+struct MsmSched {
+  uint32_t n_regular;     // buckets with 1 .. kBigBucket entries
+  uint32_t n_big;         // buckets above kBigBucket
+  uint32_t n_chunks;      // total chunk blocks of the big buckets
+  uint32_t pad;
+};
+
+// size_hist[kBigBucket - size] counts regular buckets (descending size order); big buckets are
+// compacted into big_list with their chunk ranges
+static __global__ void k_size_hist(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t* size_hist,
+                                   MsmSched* sched, uint32_t* big_list, uint32_t* big_chunk_off) {
+  __shared__ uint32_t h[kBigBucket];
+  for (int i = threadIdx.x; i < kBigBucket; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_buckets) {
+    uint32_t sz = offsets[b + 1] - offsets[b];
+    if (sz > (uint32_t)kBigBucket) {
+      uint32_t idx = atomicAdd(&sched->n_big, 1u);
+      uint32_t nch = (sz + kChunk - 1) / kChunk;
+      big_list[idx] = b;
+      big_chunk_off[idx] = atomicAdd(&sched->n_chunks, nch);
+    } else if (sz) {
+      atomicAdd(&h[kBigBucket - sz], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBigBucket; i += blockDim.x)
+    if (h[i]) atomicAdd(&size_hist[i], h[i]);
+}
+// exclusive scan of the kBigBucket size bins (one small block) -> cursors; total -> n_regular
+static __global__ void k_size_scan(uint32_t* size_hist, MsmSched* sched) {
+  if (threadIdx.x) return;
+  uint32_t run = 0;
+  for (int i = 0; i < kBigBucket; i++) { uint32_t v = size_hist[i]; size_hist[i] = run; run += v; }
+  sched->n_regular = run;
+}
+static __global__ void k_size_scatter(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t* size_cursor,
+                                      uint32_t* __restrict__ order) {
+  // warp-aggregated atomics: lanes with the same size share one atomicAdd
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t sz = b < n_buckets ? offsets[b + 1] - offsets[b] : 0;
+  bool regular = sz != 0 && sz <= (uint32_t)kBigBucket;
+  uint32_t mask = __ballot_sync(0xffffffffu, regular);
+  if (!regular) return;
+  uint32_t peers = __match_any_sync(mask, sz);
+  int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&size_cursor[kBigBucket - sz], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+  order[base + rank] = b;
+}
+// chunk -> (big bucket slot, chunk index inside the bucket)
+static __global__ void k_big_chunk_map(const uint32_t* __restrict__ offsets, const MsmSched* sched,
+                                       const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_chunk_off,
+                                       uint32_t* __restrict__ chunk_slot) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= sched->n_big) return;
+  uint32_t b = big_list[i];
+  uint32_t nch = (offsets[b + 1] - offsets[b] + kChunk - 1) / kChunk;
+  uint32_t off = big_chunk_off[i];
+  for (uint32_t k = 0; k < nch; k++) chunk_slot[off + k] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation
+// ------------------------------------------------------------------------------------------
+// one thread per regular bucket, in order of decreasing size
 template <class F>
 __global__ void __launch_bounds__(128)
-k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, uint32_t n_buckets,
-             const Affine<F>* __restrict__ table, XYZZ<F>* __restrict__ bucket_acc,
-             XYZZ<F>* __restrict__ cont, int32_t* __restrict__ cont_key, uint32_t n_threads) {
+k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+             const uint32_t* __restrict__ order, const MsmSched* __restrict__ sched,
+             const Affine<F>* __restrict__ table, XYZZ<F>* __restrict__ bucket_acc) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= n_threads) return;
-  const uint32_t total = offsets[n_buckets];
-  uint32_t start = t * kAccK;
-  if (start >= total) { cont_key[t] = -1; return; }
-  uint32_t end = min(start + (uint32_t)kAccK, total);
-  // largest b with offsets[b] <= start
-  uint32_t lo = 0, hi = n_buckets;
-  while (hi - lo > 1) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (offsets[mid] <= start) lo = mid; else hi = mid;
-  }
-  uint32_t b = lo;
-  bool is_cont = offsets[b] < start;
-  bool wrote_cont = false;
-  uint32_t next = offsets[b + 1];
+  if (t >= sched->n_regular) return;
+  uint32_t b = order[t];
+  uint32_t pos = offsets[b], end = offsets[b + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t pos = start; pos < end; pos++) {
-    if (pos == next) {
-      if (is_cont) { st_vec(&cont[t], acc); cont_key[t] = (int32_t)b; wrote_cont = true; is_cont = false; }
-      else st_vec(&bucket_acc[b], acc);
-      acc = XYZZ<F>::inf();
-      do { b++; next = offsets[b + 1]; } while (next <= pos);
+  uint32_t e = entries[pos];
+  Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
+  for (;;) {
+    pos++;
+    uint32_t e_next = 0;
+    Affine<F> p_next;
+    bool more = pos < end;
+    if (more) {                                   // fetch the next base while this one is added
+      e_next = entries[pos];
+      p_next = ld_vec(&table[e_next & 0x7fffffffu]);
     }
-    uint32_t e = entries[pos];
-    Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
     acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+    if (!more) break;
+    e = e_next;
+    p = p_next;
   }
-  if (is_cont) { st_vec(&cont[t], acc); cont_key[t] = (int32_t)b; wrote_cont = true; }
-  else st_vec(&bucket_acc[b], acc);
-  if (!wrote_cont) cont_key[t] = -1;
+  st_vec(&bucket_acc[b], acc);
 }
 
-// fold one level of continuation points (sorted by key, runs are contiguous)
-template <class F>
-__global__ void __launch_bounds__(128)
-k_fold(const XYZZ<F>* __restrict__ in_pts, const int32_t* __restrict__ in_keys, uint32_t n_in,
-       XYZZ<F>* __restrict__ out_pts, int32_t* __restrict__ out_keys, XYZZ<F>* __restrict__ bucket_acc,
-       uint32_t n_threads) {
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= n_threads) return;
-  uint32_t start = u * kFoldK;
-  if (start >= n_in) { out_keys[u] = -1; return; }
-  uint32_t end = min(start + (uint32_t)kFoldK, n_in);
-  int32_t cur = -1;
-  bool is_cont = false, wrote_cont = false;
-  XYZZ<F> acc = XYZZ<F>::inf();
-  for (uint32_t i = start; i < end; i++) {
-    int32_t k = in_keys[i];
-    if (k != cur) {
-      if (cur >= 0) {
-        if (is_cont) { st_vec(&out_pts[u], acc); out_keys[u] = cur; wrote_cont = true; }
-        else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); pt_add(t, acc); st_vec(&bucket_acc[cur], t); }
-      }
-      cur = k;
-      acc = XYZZ<F>::inf();
-      is_cont = (i == start) && start > 0 && k >= 0 && in_keys[start - 1] == k;
+// block-level tree sum of one XYZZ per thread (result valid in thread 0)
+template <class F, int THREADS>
+__device__ __forceinline__ void block_sum(XYZZ<F>& acc, XYZZ<F>* sh) {
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = THREADS / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      XYZZ<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+      pt_add(a, b);
+      sh[threadIdx.x] = a;
     }
-    if (k >= 0) { XYZZ<F> q = ld_vec_rw(&in_pts[i]); pt_add(acc, q); }
+    __syncthreads();
   }
-  if (cur >= 0) {
-    if (is_cont) { st_vec(&out_pts[u], acc); out_keys[u] = cur; wrote_cont = true; }
-    else { XYZZ<F> t = ld_vec_rw(&bucket_acc[cur]); pt_add(t, acc); st_vec(&bucket_acc[cur], t); }
+  acc = sh[0];
+}
+
+// one block per 2048-entry chunk of a big bucket -> partial[chunk]
+template <class F>
+__global__ void __launch_bounds__(kChunkThreads)
+k_big_chunks(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, const MsmSched* __restrict__ sched,
+             const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_chunk_off,
+             const uint32_t* __restrict__ chunk_slot, const Affine<F>* __restrict__ table, XYZZ<F>* __restrict__ partial) {
+  __shared__ XYZZ<F> sh[kChunkThreads];
+  for (uint32_t ch = blockIdx.x; ch < sched->n_chunks; ch += gridDim.x) {
+    uint32_t slot = chunk_slot[ch];
+    uint32_t b = big_list[slot];
+    uint32_t k = ch - big_chunk_off[slot];
+    uint32_t lo = offsets[b] + k * kChunk, hi = min(lo + (uint32_t)kChunk, offsets[b + 1]);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t pos = lo + threadIdx.x; pos < hi; pos += kChunkThreads) {    // coalesced entry reads
+      uint32_t e = entries[pos];
+      Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
+      acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+    }
+    block_sum<F, kChunkThreads>(acc, sh);
+    if (threadIdx.x == 0) st_vec(&partial[ch], acc);
+    __syncthreads();
   }
-  if (!wrote_cont) out_keys[u] = -1;
+}
+// one block per big bucket: sum its chunk partials -> bucket_acc[b]
+template <class F>
+__global__ void __launch_bounds__(kChunkThreads)
+k_big_fold(const uint32_t* __restrict__ offsets, const MsmSched* __restrict__ sched, const uint32_t* __restrict__ big_list,
+           const uint32_t* __restrict__ big_chunk_off, const XYZZ<F>* __restrict__ partial, XYZZ<F>* __restrict__ bucket_acc) {
+  __shared__ XYZZ<F> sh[kChunkThreads];
+  for (uint32_t slot = blockIdx.x; slot < sched->n_big; slot += gridDim.x) {
+    uint32_t b = big_list[slot];
+    uint32_t nch = (offsets[b + 1] - offsets[b] + kChunk - 1) / kChunk;
+    const XYZZ<F>* src = partial + big_chunk_off[slot];
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = threadIdx.x; k < nch; k += kChunkThreads) {
+      XYZZ<F> q = ld_vec_rw(&src[k]);
+      pt_add(acc, q);
+    }
+    block_sum<F, kChunkThreads>(acc, sh);
+    if (threadIdx.x == 0) st_vec(&bucket_acc[b], acc);
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
-// bucket reduction: out[u] = sum_{b in chunk u} (b + 1) * bucket[b]   (b = index inside its set)
+// bucket reduction through row / column sums
 // ------------------------------------------------------------------------------------------
+// out[set][o] = sum_{k < K} in[set][(o / inner) * outer_stride + (o % inner) * inner_stride + k * step]
 template <class F>
 __global__ void __launch_bounds__(128)
-k_bucket_reduce(const XYZZ<F>* __restrict__ bucket_acc, uint32_t B, uint32_t n_sets, XYZZ<F>* __restrict__ out) {
-  uint32_t chunks_per_set = (B + kRedM - 1) / kRedM;
-  uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-  if (u >= chunks_per_set * n_sets) return;
-  uint32_t set = u / chunks_per_set, ch = u % chunks_per_set;
-  uint32_t b0 = ch * kRedM;
-  uint32_t b1 = min(b0 + (uint32_t)kRedM, B);
-  const XYZZ<F>* src = bucket_acc + (size_t)set * B;
-  XYZZ<F> running = XYZZ<F>::inf(), acc = XYZZ<F>::inf();
-  for (uint32_t b = b1; b-- > b0;) {
-    XYZZ<F> q = ld_vec_rw(&src[b]);
-    pt_add(running, q);
-    pt_add(acc, running);
+k_seg_sum(const XYZZ<F>* __restrict__ in, size_t in_set_stride, XYZZ<F>* __restrict__ out, uint32_t n_out, uint32_t inner,
+          uint32_t inner_stride, uint32_t outer_stride, uint32_t step, uint32_t K) {
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  const XYZZ<F>* src = in + (size_t)blockIdx.y * in_set_stride + (size_t)(o / inner) * outer_stride +
+                       (size_t)(o % inner) * inner_stride;
+  XYZZ<F> acc = ld_vec_rw(src);
+  for (uint32_t k = 1; k < K; k++) {
+    XYZZ<F> q = ld_vec_rw(src + (size_t)k * step);
+    pt_add(acc, q);
   }
-  if (b0 && !running.is_inf()) { XYZZ<F> m = XYZZ<F>::mul_u32(running, b0); pt_add(acc, m); }
-  st_vec(&out[u], acc);
+  st_vec(&out[(size_t)blockIdx.y * n_out + o], acc);
+}
+// weighted[set][i] = (i * L) * rows[set][i] for i < H;  weighted[set][H + j] = (j + 1) * cols[set][j] for j < L
+template <class F>
+__global__ void __launch_bounds__(128)
+k_weight_rows_cols(const XYZZ<F>* __restrict__ rows, const XYZZ<F>* __restrict__ cols, uint32_t H, uint32_t L,
+                   XYZZ<F>* __restrict__ weighted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H + L) return;
+  uint32_t set = blockIdx.y;
+  XYZZ<F> p = i < H ? ld_vec_rw(&rows[(size_t)set * H + i]) : ld_vec_rw(&cols[(size_t)set * L + (i - H)]);
+  uint32_t k = i < H ? i * L : (i - H) + 1;
+  XYZZ<F> r = XYZZ<F>::inf();
+  if (k && !p.is_inf()) r = XYZZ<F>::mul_u32(p, k);
+  st_vec(&weighted[(size_t)set * (H + L) + i], r);
 }
 
 // out[set][blockIdx.x] = sum of a slice of in[set][...]
@@ -356,7 +455,9 @@ struct MsmEngine {
     cudaStream_t st = ctx->main;
     size_t n = srs->n;
     srs->precomp = (flags & ZKB_SRS_PRECOMPUTE) ? 1 : 0;
-    srs->c = msm_pick_c(n, srs->precomp);
+    size_t n_eff = 0;                    // identity bases never produce bucket entries
+    for (size_t i = 0; i < n; i++) n_eff += h_inf[i] ? 0 : 1;
+    srs->c = msm_pick_c(n_eff, srs->precomp);
     srs->W = msm_windows(FrP::BITS, srs->c);
     if (srs->precomp && (size_t)srs->W * n >= (size_t(1) << 31))
       return set_err(ctx, ZKB_E_INVALID, "precomputed table too large for 31-bit indices");
@@ -409,47 +510,95 @@ struct MsmEngine {
     ZKB_LAUNCH(ctx, (k_digits<true, Fr>), dig_blocks, 256, 0, st, d_scalars, (uint32_t)n, srs->inf, g,
                (uint32_t)base_offset, scalars_mont, cursor, entries);
 
+    // schedule: regular buckets by decreasing size, big buckets in chunks
+    uint32_t *size_hist, *order, *big_list, *big_chunk_off, *chunk_slot;
+    MsmSched* sched;
+    const uint32_t max_big = (uint32_t)(max_entries / (kBigBucket + 1)) + 1;
+    const uint32_t max_chunks = (uint32_t)(max_entries / kChunk) + max_big;
+    ZKB_TRY(ws.alloc(&size_hist, (size_t)kBigBucket + 4));      // bins followed by the MsmSched block
+    sched = reinterpret_cast<MsmSched*>(size_hist + kBigBucket);
+    ZKB_TRY(ws.alloc(&order, n_buckets));
+    ZKB_TRY(ws.alloc(&big_list, max_big));
+    ZKB_TRY(ws.alloc(&big_chunk_off, max_big));
+    ZKB_TRY(ws.alloc(&chunk_slot, max_chunks));
+    ZKB_CUDA(ctx, cudaMemsetAsync(size_hist, 0, sizeof(uint32_t) * (kBigBucket + 4), st));
+    ZKB_LAUNCH(ctx, k_size_hist, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, size_hist, sched, big_list,
+               big_chunk_off);
+    ZKB_LAUNCH(ctx, k_size_scan, 1, 32, 0, st, size_hist, sched);
+    ZKB_LAUNCH(ctx, k_size_scatter, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, size_hist, order);
+    ZKB_LAUNCH(ctx, k_big_chunk_map, ceil_div(max_big, 256), 256, 0, st, offsets, sched, big_list, big_chunk_off, chunk_slot);
+
     // accumulate
-    Pt *bucket_acc, *cont_a, *cont_b;
-    int32_t *key_a, *key_b;
-    const uint32_t n_acc_threads = ceil_div(max_entries, kAccK);
-    const uint32_t n_fold1 = ceil_div(n_acc_threads, kFoldK);
+    Pt *bucket_acc, *partial;
     ZKB_TRY(ws.alloc(&bucket_acc, n_buckets));
-    ZKB_TRY(ws.alloc(&cont_a, n_acc_threads));
-    ZKB_TRY(ws.alloc(&key_a, n_acc_threads));
-    ZKB_TRY(ws.alloc(&cont_b, n_fold1));
-    ZKB_TRY(ws.alloc(&key_b, n_fold1));
-    ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));
+    ZKB_TRY(ws.alloc(&partial, max_chunks));
+    ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
     prof_begin(ctx, st);
-    ZKB_LAUNCH(ctx, (k_accumulate<F>), ceil_div(n_acc_threads, 128), 128, 0, st, entries, offsets, n_buckets,
-               (const Aff*)srs->table, bucket_acc, cont_a, key_a, n_acc_threads);
+    ZKB_LAUNCH(ctx, (k_accumulate<F>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+               (const Aff*)srs->table, bucket_acc);
     prof_end(ctx, st, (double)n * (32.0 + sizeof(Aff)));   // one read of each (scalar, base) pair
     {
-      uint32_t n_in = n_acc_threads;
-      Pt *pin = cont_a, *pout = cont_b;
-      int32_t *kin = key_a, *kout = key_b;
-      while (n_in > 1) {
-        uint32_t n_out = ceil_div(n_in, kFoldK);
-        ZKB_LAUNCH(ctx, (k_fold<F>), ceil_div(n_out, 128), 128, 0, st, pin, kin, n_in, pout, kout, bucket_acc, n_out);
-        std::swap(pin, pout);
-        std::swap(kin, kout);
-        n_in = n_out;
-      }
+      // grids are upper bounds read against device-side counts (no host round trip)
+      unsigned chunk_blocks = max_chunks < (unsigned)ctx->sm_count * 8 ? max_chunks : ctx->sm_count * 8;
+      unsigned fold_blocks = max_big < (unsigned)ctx->sm_count * 4 ? max_big : ctx->sm_count * 4;
+      ZKB_LAUNCH(ctx, (k_big_chunks<F>), chunk_blocks, kChunkThreads, 0, st, entries, offsets, sched, big_list,
+                 big_chunk_off, chunk_slot, (const Aff*)srs->table, partial);
+      ZKB_LAUNCH(ctx, (k_big_fold<F>), fold_blocks, kChunkThreads, 0, st, offsets, sched, big_list, big_chunk_off,
+                 (const Pt*)partial, bucket_acc);
     }
-    // reduce
-    const uint32_t chunks_per_set = ceil_div(g.B, kRedM);
-    Pt *red_a, *red_b;
-    ZKB_TRY(ws.alloc(&red_a, (size_t)chunks_per_set * g.n_sets));
-    ZKB_TRY(ws.alloc(&red_b, (size_t)ceil_div(chunks_per_set, 64) * g.n_sets + 1));
-    ZKB_LAUNCH(ctx, (k_bucket_reduce<F>), ceil_div((size_t)chunks_per_set * g.n_sets, 128), 128, 0, st, bucket_acc,
-               g.B, g.n_sets, red_a);
-    uint32_t n_per = chunks_per_set;
-    Pt *pin = red_a, *pout = red_b;
+
+    // reduce: bucket b = hi * L + lo carries weight b + 1 = hi * L + (lo + 1)
+    const unsigned lo_bits = (unsigned)(g.c - 1) / 2, hi_bits = (unsigned)(g.c - 1) - lo_bits;
+    const uint32_t L = 1u << lo_bits, H = 1u << hi_bits;
+    Pt *tmp_a, *tmp_b, *rows, *cols, *weighted;
+    ZKB_TRY(ws.alloc(&tmp_a, (size_t)g.n_sets * (g.B / 2 + 1)));
+    ZKB_TRY(ws.alloc(&tmp_b, (size_t)g.n_sets * (g.B / 4 + 1)));
+    ZKB_TRY(ws.alloc(&rows, (size_t)g.n_sets * H));
+    ZKB_TRY(ws.alloc(&cols, (size_t)g.n_sets * L));
+    ZKB_TRY(ws.alloc(&weighted, (size_t)g.n_sets * (H + L)));
+    auto reduce_axis = [&](bool along_rows, Pt* final_out) -> int {
+      // along_rows: sum over lo (length L) for every hi; else sum over hi (length H) for every lo
+      uint32_t len = along_rows ? L : H;          // remaining length of the reduced axis
+      const uint32_t other = along_rows ? H : L;
+      const Pt* in = bucket_acc;
+      size_t in_set_stride = g.B;
+      if (len == 1) {
+        ZKB_LAUNCH(ctx, (k_seg_sum<F>), dim3(ceil_div(other, 128), g.n_sets), 128, 0, st, in, in_set_stride, final_out,
+                   other, other, 1u, 1u, 1u, 1u);
+        return ZKB_OK;
+      }
+      Pt* bufs[2] = {tmp_a, tmp_b};
+      int flip = 0;
+      while (len > 1) {
+        uint32_t K = len < (uint32_t)kSegK ? len : (uint32_t)kSegK;
+        uint32_t new_len = len / K;                 // powers of two throughout
+        uint32_t n_out = new_len * other;
+        Pt* out = new_len == 1 ? final_out : bufs[flip];
+        if (along_rows)      // element (hi, j) of a [other][len] matrix; output [other][new_len]
+          ZKB_LAUNCH(ctx, (k_seg_sum<F>), dim3(ceil_div(n_out, 128), g.n_sets), 128, 0, st, in, in_set_stride, out, n_out,
+                     new_len, K, len, 1u, K);
+        else                 // element (i, lo) of a [len][other] matrix; output [new_len][other]
+          ZKB_LAUNCH(ctx, (k_seg_sum<F>), dim3(ceil_div(n_out, 128), g.n_sets), 128, 0, st, in, in_set_stride, out, n_out,
+                     other, 1u, K * other, other, K);
+        in = out;
+        in_set_stride = n_out;
+        len = new_len;
+        flip ^= 1;
+      }
+      return ZKB_OK;
+    };
+    ZKB_TRY(reduce_axis(true, rows));
+    ZKB_TRY(reduce_axis(false, cols));
+    ZKB_LAUNCH(ctx, (k_weight_rows_cols<F>), dim3(ceil_div(H + L, 128), g.n_sets), 128, 0, st, (const Pt*)rows,
+               (const Pt*)cols, H, L, weighted);
+    uint32_t n_per = H + L;
+    Pt *pin = weighted, *pout = tmp_a;
     while (n_per > 1) {
       uint32_t per_thread = n_per > 64 * 64 ? 4 : 1;
       uint32_t n_blocks = ceil_div(n_per, 64 * per_thread);
       ZKB_LAUNCH(ctx, (k_sum_points<F>), dim3(n_blocks, g.n_sets), 64, 0, st, pin, n_per, pout, per_thread);
-      std::swap(pin, pout);
+      pin = pout;
+      pout = pout == tmp_a ? tmp_b : tmp_a;
       n_per = n_blocks;
     }
     if (g.n_sets > 1) {

@@ -142,3 +142,28 @@ def test_msm_linearity_large(ctx):
     got_st = H.array_point(cid, group, out, is_inf)
     assert got_st == c.to_affine(c.add(c.from_affine(got_s), c.from_affine(got_t)))
     srs.free()
+
+
+@pytest.mark.parametrize("cid,group", [(BN254, 1), (BLS12_381, 2)])
+@pytest.mark.parametrize("precompute", [True, False])
+def test_msm_giant_bucket(ctx, cid, group, precompute):
+    """Thousands of equal scalars land in one bucket: the chunked big-bucket path with several
+    2048-entry chunks (and the fold over their partials) must agree with the CPU restatement."""
+    from oracle import cref
+    c = CURVES[(cid, group)]
+    n = 7000 if group == 1 else 6000
+    rng = np.random.default_rng(n)
+    gen_xy, _ = H.points_array(cid, group, [c.gen])
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    ks[:, 0] = rng.integers(1, 1 << 40, size=n, dtype=np.uint64)
+    xy, inf = ctx.fixed_base_mul(cid, group, gen_xy[0], ks)
+    sc = np.zeros((n, 4), dtype=np.uint64)
+    sc[:, 0] = 1                                            # digit 1 of window 0 for most entries
+    sc[5000:5600, 0] = 0x0007000700070007                   # the same non-trivial digit in several windows
+    sc[5600:] = rng.integers(0, 1 << 62, size=(n - 5600, 4), dtype=np.uint64)
+    sc[5600:, 3] &= np.uint64((1 << 60) - 1)
+    srs = ctx.srs_upload(cid, group, xy, inf, precompute=precompute)
+    got, ginf = ctx.msm(srs, sc)
+    want, winf, _ = cref.msm(cid, group, xy, inf, sc)
+    assert ginf == winf and np.array_equal(got, want)
+    srs.free()
