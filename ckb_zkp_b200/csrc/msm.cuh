@@ -11,7 +11,7 @@
 //     array: no per-window reduction and no doubling chain at the end;
 //   * counting sort of (bucket, base index) pairs: histogram -> exclusive scan -> scatter;
 //   * bucket accumulation: one thread per bucket, buckets ordered by decreasing size so the
-//     32 lanes of a warp run the same trip count; buckets above kBigBucket entries
+//     32 lanes of a warp run the same trip count; buckets above a runtime threshold
 //     (boolean-heavy witnesses put a large share of all entries into the "digit = 1" bucket)
 //     are cut into 2048-entry chunks, one block each, and folded by a second block-level pass;
 //   * bucket reduction sum_b (b + 1) * S_b through the row / column sums of the bucket array
@@ -35,9 +35,10 @@ struct zkb_srs {
 
 namespace zkb {
 
-constexpr int kBigBucket = 256;         // buckets with more entries take the chunked path
+constexpr int kSizeBins = 4096;         // regular buckets hold 1 .. big_threshold <= kSizeBins entries
+constexpr int kMinBigBucket = 256;      // lower clamp of the runtime big-bucket threshold
 constexpr int kChunkThreads = 128;      // threads per big-bucket chunk block
-constexpr int kChunkPer = 16;           // entries per thread in a chunk
+constexpr int kChunkPer = 32;           // entries per thread in a chunk
 constexpr int kChunk = kChunkThreads * kChunkPer;
 constexpr int kSegK = 8;                // points summed per thread in the row / column passes
 constexpr int kScalarLimbs = 8;
@@ -167,54 +168,67 @@ static __global__ void k_scan_finish(uint32_t* offsets, uint32_t n, const uint32
 // bucket scheduling: order the regular buckets by decreasing size, list the big ones
 // ------------------------------------------------------------------------------------------
 struct MsmSched {
-  uint32_t n_regular;     // buckets with 1 .. kBigBucket entries
-  uint32_t n_big;         // buckets above kBigBucket
+  uint32_t n_regular;     // buckets with 1 .. big_threshold entries
+  uint32_t n_big;         // buckets above big_threshold
   uint32_t n_chunks;      // total chunk blocks of the big buckets
   uint32_t pad;
 };
+// A bucket is "big" when one thread adding it sequentially would stretch the kernel's critical path:
+// a lone warp retires a mixed addition in ~7 us, the whole grid ~2.6 G of them per second, so a bucket
+// may hold up to ~entries / 32768 entries before it is worth cutting it into chunks.
+inline uint32_t msm_big_threshold(size_t max_entries) {
+  size_t t = max_entries >> 15;
+  if (t < (size_t)kMinBigBucket) t = kMinBigBucket;
+  if (t > (size_t)kSizeBins) t = kSizeBins;
+  return (uint32_t)t;
+}
 
-// size_hist[kBigBucket - size] counts regular buckets (descending size order); big buckets are
-// compacted into big_list with their chunk ranges
-static __global__ void k_size_hist(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t* size_hist,
-                                   MsmSched* sched, uint32_t* big_list, uint32_t* big_chunk_off) {
-  __shared__ uint32_t h[kBigBucket];
-  for (int i = threadIdx.x; i < kBigBucket; i += blockDim.x) h[i] = 0;
+// size_hist[big - size] counts regular buckets (descending size order); big buckets are compacted
+// into big_list with their chunk ranges
+static __global__ void k_size_hist(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t big,
+                                   uint32_t* size_hist, MsmSched* sched, uint32_t* big_list, uint32_t* big_chunk_off) {
+  __shared__ uint32_t h[kSizeBins];
+  for (uint32_t i = threadIdx.x; i < big; i += blockDim.x) h[i] = 0;
   __syncthreads();
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < n_buckets) {
+  for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n_buckets; b += gridDim.x * blockDim.x) {
     uint32_t sz = offsets[b + 1] - offsets[b];
-    if (sz > (uint32_t)kBigBucket) {
+    if (sz > big) {
       uint32_t idx = atomicAdd(&sched->n_big, 1u);
       uint32_t nch = (sz + kChunk - 1) / kChunk;
       big_list[idx] = b;
       big_chunk_off[idx] = atomicAdd(&sched->n_chunks, nch);
     } else if (sz) {
-      atomicAdd(&h[kBigBucket - sz], 1u);
+      atomicAdd(&h[big - sz], 1u);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < kBigBucket; i += blockDim.x)
+  for (uint32_t i = threadIdx.x; i < big; i += blockDim.x)
     if (h[i]) atomicAdd(&size_hist[i], h[i]);
 }
-// exclusive scan of the kBigBucket size bins (one small block) -> cursors; total -> n_regular
-static __global__ void k_size_scan(uint32_t* size_hist, MsmSched* sched) {
-  if (threadIdx.x) return;
-  uint32_t run = 0;
-  for (int i = 0; i < kBigBucket; i++) { uint32_t v = size_hist[i]; size_hist[i] = run; run += v; }
-  sched->n_regular = run;
+// exclusive scan of the size bins (one block of 1024 threads, 4 bins each) -> cursors; total -> n_regular
+static __global__ void k_size_scan(uint32_t* size_hist, uint32_t big, MsmSched* sched) {
+  uint32_t v[4], sum = 0;
+  uint32_t base = threadIdx.x * 4;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { v[i] = base + i < big ? size_hist[base + i] : 0; sum += v[i]; }
+  uint32_t total;
+  uint32_t off = block_exclusive_scan(sum, &total);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { if (base + i < big) size_hist[base + i] = off; off += v[i]; }
+  if (threadIdx.x == 0) sched->n_regular = total;
 }
-static __global__ void k_size_scatter(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t* size_cursor,
-                                      uint32_t* __restrict__ order) {
+static __global__ void k_size_scatter(const uint32_t* __restrict__ offsets, uint32_t n_buckets, uint32_t big,
+                                      uint32_t* size_cursor, uint32_t* __restrict__ order) {
   // warp-aggregated atomics: lanes with the same size share one atomicAdd
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t sz = b < n_buckets ? offsets[b + 1] - offsets[b] : 0;
-  bool regular = sz != 0 && sz <= (uint32_t)kBigBucket;
+  bool regular = sz != 0 && sz <= big;
   uint32_t mask = __ballot_sync(0xffffffffu, regular);
   if (!regular) return;
   uint32_t peers = __match_any_sync(mask, sz);
   int leader = __ffs(peers) - 1;
   uint32_t base = 0;
-  if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&size_cursor[kBigBucket - sz], __popc(peers));
+  if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&size_cursor[big - sz], __popc(peers));
   base = __shfl_sync(peers, base, leader);
   uint32_t rank = __popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
   order[base + rank] = b;
@@ -433,16 +447,25 @@ k_precompute(Affine<F>* table, uint32_t n, int c, int W) {
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
-inline int msm_pick_c(size_t n, int precomp) {
-  int l = (int)ceil_log2(n < 2 ? 2 : n);
-  int c = precomp ? l : (l > 4 ? l - 3 : 2);     // few bucket sets vs W bucket sets
-  if (precomp) { if (c > 20) c = 20; } else { if (c > 16) c = 16; }
-  if (c < 4) c = 4;
+// Window width from a cost model in field multiplications: n * W mixed additions (10 mul) plus the
+// bucket reduction, ~2.3 full additions (14 mul) per bucket of every bucket set.
+inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
+  if (n < 2) n = 2;
+  int best_c = 4;
+  double best = 1e300;
+  const int c_max = precomp ? 23 : 16;
+  for (int c = 4; c <= c_max; c++) {
+    int W = msm_windows(scalar_bits, c);
+    double sets = precomp ? 1.0 : (double)W;
+    double cost = (double)n * W * 10.0 + sets * (double)(size_t(1) << (c - 1)) * 32.0;
+    if (!precomp) cost += (double)W * c * 9.0;      // doubling chain of the window combine (negligible)
+    if (cost < best) { best = cost; best_c = c; }
+  }
   if (const char* e = getenv(precomp ? "ZKB_MSM_C" : "ZKB_MSM_C_NOPRE")) {
     int v = atoi(e);
-    if (v >= 2 && v <= 23) c = v;
+    if (v >= 2 && v <= 23) best_c = v;
   }
-  return c;
+  return best_c;
 }
 
 template <class F, class FrP>
@@ -457,7 +480,7 @@ struct MsmEngine {
     srs->precomp = (flags & ZKB_SRS_PRECOMPUTE) ? 1 : 0;
     size_t n_eff = 0;                    // identity bases never produce bucket entries
     for (size_t i = 0; i < n; i++) n_eff += h_inf[i] ? 0 : 1;
-    srs->c = msm_pick_c(n_eff, srs->precomp);
+    srs->c = msm_pick_c(n_eff, srs->precomp, FrP::BITS);
     srs->W = msm_windows(FrP::BITS, srs->c);
     if (srs->precomp && (size_t)srs->W * n >= (size_t(1) << 31))
       return set_err(ctx, ZKB_E_INVALID, "precomputed table too large for 31-bit indices");
@@ -513,19 +536,24 @@ struct MsmEngine {
     // schedule: regular buckets by decreasing size, big buckets in chunks
     uint32_t *size_hist, *order, *big_list, *big_chunk_off, *chunk_slot;
     MsmSched* sched;
-    const uint32_t max_big = (uint32_t)(max_entries / (kBigBucket + 1)) + 1;
+    const uint32_t big = msm_big_threshold(max_entries);
+    const uint32_t max_big = (uint32_t)(max_entries / (big + 1)) + 1;
     const uint32_t max_chunks = (uint32_t)(max_entries / kChunk) + max_big;
-    ZKB_TRY(ws.alloc(&size_hist, (size_t)kBigBucket + 4));      // bins followed by the MsmSched block
-    sched = reinterpret_cast<MsmSched*>(size_hist + kBigBucket);
+    ZKB_TRY(ws.alloc(&size_hist, (size_t)kSizeBins + 4));       // bins followed by the MsmSched block
+    sched = reinterpret_cast<MsmSched*>(size_hist + kSizeBins);
     ZKB_TRY(ws.alloc(&order, n_buckets));
     ZKB_TRY(ws.alloc(&big_list, max_big));
     ZKB_TRY(ws.alloc(&big_chunk_off, max_big));
     ZKB_TRY(ws.alloc(&chunk_slot, max_chunks));
-    ZKB_CUDA(ctx, cudaMemsetAsync(size_hist, 0, sizeof(uint32_t) * (kBigBucket + 4), st));
-    ZKB_LAUNCH(ctx, k_size_hist, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, size_hist, sched, big_list,
-               big_chunk_off);
-    ZKB_LAUNCH(ctx, k_size_scan, 1, 32, 0, st, size_hist, sched);
-    ZKB_LAUNCH(ctx, k_size_scatter, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, size_hist, order);
+    ZKB_CUDA(ctx, cudaMemsetAsync(size_hist, 0, sizeof(uint32_t) * (kSizeBins + 4), st));
+    {
+      unsigned hist_blocks = ceil_div(n_buckets, 1024);
+      if (hist_blocks > (unsigned)ctx->sm_count * 2) hist_blocks = ctx->sm_count * 2;
+      ZKB_LAUNCH(ctx, k_size_hist, hist_blocks, 1024, 0, st, offsets, n_buckets, big, size_hist, sched, big_list,
+                 big_chunk_off);
+    }
+    ZKB_LAUNCH(ctx, k_size_scan, 1, 1024, 0, st, size_hist, big, sched);
+    ZKB_LAUNCH(ctx, k_size_scatter, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, big, size_hist, order);
     ZKB_LAUNCH(ctx, k_big_chunk_map, ceil_div(max_big, 256), 256, 0, st, offsets, sched, big_list, big_chunk_off, chunk_slot);
 
     // accumulate

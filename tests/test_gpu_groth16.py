@@ -147,3 +147,38 @@ def test_error_behaviour(ctx):
         ctx.groth16_h(BN254, bad, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]))
     with pytest.raises(ValueError):
         ctx.groth16_h(BN254, A, B, C, g["z"][:-1], int(g["n_inputs"]), int(g["n_aux"]))
+
+
+def test_full_size_witness_map_and_proof(ctx):
+    """BASELINE configs[1] shape at 2^17 constraints (domain 2^18): h bit-exact against the C++
+    restatement, the proof bit-exact against the C++ prover on the same synthetic key, and the
+    proof equal to the in-the-exponent derivation."""
+    from ckb_zkp_b200 import synth
+    from oracle import cref
+    cid, n = BLS12_381, 1 << 17
+    inst = synth.MimcInstance(cid, n)
+    A, B, C, z = inst.device_form(ctx)
+    h = ctx.groth16_h(cid, A, B, C, z, inst.n_inputs, inst.n_aux)
+    mats = [(m.row_ptr, m.col_idx, m.coeff) for m in (A, B, C)]
+    want_h = cref.witness_map(cid, mats[0], mats[1], mats[2], z, inst.n_inputs)
+    assert np.array_equal(h, want_h)
+    assert not h[-1].any()                      # satisfied witness: top coefficient of h is zero
+    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, len(h), b_zero_cols=np.arange(4, 4 + n, 2))
+    params = key.upload(ctx, cid)
+    r, s = synth.ints_to_limbs([0xABCDEF123]), synth.ints_to_limbs([0x13579BDF])
+    proof = ctx.groth16_prove(params.pk, A, B, C, z, inst.n_inputs, inst.n_aux, r[0], s[0])
+    # in the exponent
+    ea, eb, ec = key.expected_exponents(inst.p, inst.z, synth.limbs_to_ints(h), 0xABCDEF123, 0x13579BDF)
+    for grp, e, got in ((1, ea, proof[0]), (2, eb, proof[1]), (1, ec, proof[2])):
+        xy, inf = ctx.fixed_base_mul(cid, grp, synth.generator_mont(cid, grp), synth.ints_to_limbs([e]))
+        assert not got[1] and not inf[0] and np.array_equal(xy[0], got[0])
+    # against the CPU restatement of the reference prover on the same key
+    g1, g2 = synth.generator_mont(cid, 1), synth.generator_mont(cid, 2)
+    pts = lambda grp, k: cref.fixed_base_mul(cid, grp, g1 if grp == 1 else g2, k)
+    pk = {"a": pts(1, key.a), "b1": pts(1, key.b), "b2": pts(2, key.b), "h": pts(1, key.h), "l": pts(1, key.l),
+          "g1_singles": pts(1, np.stack([key.alpha, key.beta, key.delta]))[0],
+          "g2_singles": pts(2, np.stack([key.beta, key.delta]))[0]}
+    ref = cref.groth16_prove(cid, pk, mats[0], mats[1], mats[2], z, inst.n_inputs, inst.n_aux, r[0], s[0])
+    for got, want in zip(proof, ref):
+        assert got[1] == want[1] and np.array_equal(got[0], want[0])
+    params.free()

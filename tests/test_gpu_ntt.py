@@ -45,7 +45,7 @@ def test_ntt_is_the_dft(ctx, cid):
 
 
 @pytest.mark.parametrize("cid", [BN254, BLS12_381])
-@pytest.mark.parametrize("log_n", [16, 20, 22])
+@pytest.mark.parametrize("log_n", [16, 19, 20, 21, 22, 24])
 def test_ntt_large_properties(ctx, cid, log_n):
     """Sizes of the BASELINE sweep: round trips, and evaluation of a sparse polynomial whose
     transform is known in closed form (a*x^j -> a*w^(ij))."""
@@ -88,3 +88,18 @@ def test_ntt_too_large(ctx):
     arr = np.zeros((2, 4), dtype=np.uint64)
     with pytest.raises((ZkbError, ValueError)):
         ctx.ntt(BN254, arr, 29)
+
+
+@pytest.mark.parametrize("cid,log_n", [(BN254, 17), (BLS12_381, 21)])
+def test_ntt_large_vs_cpu_restatement(ctx, cid, log_n):
+    """bit-exact against the C++ restatement of ark-poly's radix-2 domain at sizes the Python oracle
+    cannot reach (2^21 = the domain of the 2^20-constraint proof)"""
+    from oracle import cref
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n)
+    a = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    for kw in ({}, {"inverse": True, "coset": True}):
+        got = ctx.ntt(cid, a.copy(), log_n, **kw)
+        want = cref.ntt(cid, a.copy(), log_n, **kw)
+        assert np.array_equal(got, want), kw
