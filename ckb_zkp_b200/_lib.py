@@ -59,6 +59,9 @@ SIGNATURES = {
     "zkb_groth16_fetch_proof": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "zkb_fixed_base_mul": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zkb_fr_convert": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int]),
+    "zkb_poly_div_linear": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "zkb_poly_lincomb": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "zkb_fr_batch_inverse": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t]),
     "zkb_debug_fp_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_debug_pt_op": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t]),
 }

@@ -194,6 +194,44 @@ class Context:
         self._check(self.lib.zkb_fr_convert(self.handle, curve, _ptr(a), _ptr(out), a.shape[0], 1 if to_mont else 0))
         return out
 
+    # -- polynomial helpers (Marlin) ---------------------------------------------------------------
+    def poly_div_linear(self, curve, p_mont, z_mont, want_quotient=True):
+        """(q, rem): q = p / (x - z) (n - 1 coefficients) and rem = p(z); all Montgomery uint64[., 4]"""
+        p = _fr(p_mont, "polynomial")
+        z = np.ascontiguousarray(z_mont, dtype=np.uint64).reshape(4)
+        n = p.shape[0]
+        q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64) if want_quotient else None
+        rem = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.zkb_poly_div_linear(self.handle, curve, _ptr(p), n, _ptr(z),
+                                                 _ptr(q) if (want_quotient and n > 1) else None, _ptr(rem)))
+        return q, rem
+
+    def poly_eval(self, curve, p_mont, z_mont):
+        return self.poly_div_linear(curve, p_mont, z_mont, want_quotient=False)[1]
+
+    def poly_lincomb(self, curve, polys, coeffs_mont, shifts=None, out_len=None):
+        """sum_j coeffs[j] * x^shifts[j] * polys[j] as uint64[out_len, 4]"""
+        polys = [_fr(p, "polynomial") for p in polys]
+        k = len(polys)
+        shifts = [0] * k if shifts is None else list(shifts)
+        if out_len is None:
+            out_len = max([len(p) + s for p, s in zip(polys, shifts)] + [0])
+        coeffs = _fr(coeffs_mont, "coefficients")
+        if coeffs.shape[0] != k:
+            raise ValueError("one coefficient per polynomial")
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[p.ctypes.data for p in polys])
+        lens = (ctypes.c_size_t * max(k, 1))(*[len(p) for p in polys])
+        shs = (ctypes.c_size_t * max(k, 1))(*shifts)
+        out = np.zeros((out_len, 4), dtype=np.uint64)
+        self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), _ptr(out), out_len))
+        return out
+
+    def fr_batch_inverse(self, curve, a_mont):
+        a = _fr(a_mont, "elements")
+        out = np.zeros_like(a)
+        self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, _ptr(a), _ptr(out), a.shape[0]))
+        return out
+
     # -- Groth16 ------------------------------------------------------------------------------
     def groth16_h(self, curve, A, B, C, z_mont, n_inputs, n_aux):
         z = _fr(z_mont, "assignment")

@@ -1,0 +1,267 @@
+// Polynomial helpers over Fr used by the Marlin prover around its MSM / NTT calls
+// (kernel group K7):
+//   * division by (x - z) and evaluation at z   -- KZG10::compute_witness_polynomial
+//     (marlin/src/pc/kzg10.rs:211-226) and the evaluations of marlin/src/lib.rs:147-156
+//   * linear combination of (shifted) polynomials -- PC::open (marlin/src/pc/mod.rs:85-98)
+//   * batch inversion                             -- ark_ff::batch_inversion as used in
+//     marlin/src/ahp/prover.rs:365-367 and marlin/src/ahp/arithmetic.rs:28-34
+//
+// Division by a linear factor is the suffix recurrence H_j = p_j + z * H_(j+1) (q_(j-1) = H_j,
+// remainder H_0 = p(z)).  It is evaluated as a tree: an upward pass collapses chunks of 64
+// coefficients into their local Horner values with the multiplier z^(64^level), a downward pass
+// re-expands the suffix values from the carry of the next chunk -- O(n) work, log_64(n) launches.
+#include <cstring>
+
+#include "common.cuh"
+#include "devutil.cuh"
+#include "field.cuh"
+
+namespace zkb {
+
+constexpr int kPolyChunk = 64;
+constexpr int kMaxLevels = 8;
+constexpr int kMaxLincomb = 64;
+
+// zp[l] = z^(64^l)
+template <class FrP>
+__global__ void k_poly_zpows(Fp<FrP> z, int levels, Fp<FrP>* zp) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x | blockIdx.x) return;
+  Fr cur = z;
+  for (int l = 0; l < levels; l++) {
+    zp[l] = cur;
+    for (int i = 0; i < 6; i++) cur = Fr::sqr(cur);      // ^64
+  }
+}
+// up[c] = sum_i in[c*64 + i] * zl^i
+template <class FrP>
+__global__ void __launch_bounds__(128)
+k_poly_up(const Fp<FrP>* __restrict__ in, size_t n, const Fp<FrP>* __restrict__ zl_p, Fp<FrP>* __restrict__ up,
+          size_t n_chunks) {
+  using Fr = Fp<FrP>;
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const Fr zl = *zl_p;
+  size_t lo = c * kPolyChunk, hi = lo + kPolyChunk < n ? lo + kPolyChunk : n;
+  Fr acc = Fr::zero();
+  for (size_t j = hi; j-- > lo;) acc = Fr::add(Fr::mul(acc, zl), ld_vec_rw(&in[j]));
+  st_vec(&up[c], acc);
+}
+// suffix values of one level: H[j] = in[j] + zl * H[j+1], the carry into a chunk's top element being
+// the suffix value of the next chunk one level up (0 past the end).  At level 0 the values are the
+// quotient coefficients shifted by one (q[j-1] = H[j]) and H[0] is the remainder p(z).
+template <class FrP>
+__global__ void __launch_bounds__(128)
+k_poly_down(const Fp<FrP>* __restrict__ in, size_t n, const Fp<FrP>* __restrict__ zl_p, const Fp<FrP>* __restrict__ upper_H,
+            size_t n_chunks, Fp<FrP>* __restrict__ H, int level0, Fp<FrP>* __restrict__ q, Fp<FrP>* __restrict__ rem) {
+  using Fr = Fp<FrP>;
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_chunks) return;
+  const Fr zl = *zl_p;
+  size_t lo = c * kPolyChunk, hi = lo + kPolyChunk < n ? lo + kPolyChunk : n;
+  Fr carry = (upper_H && c + 1 < n_chunks) ? ld_vec_rw(&upper_H[c + 1]) : Fr::zero();
+  for (size_t j = hi; j-- > lo;) {
+    carry = Fr::add(Fr::mul(carry, zl), ld_vec_rw(&in[j]));
+    if (level0) {
+      if (j == 0) { if (rem) st_vec(rem, carry); }
+      else if (q) st_vec(&q[j - 1], carry);
+    } else {
+      st_vec(&H[j], carry);
+    }
+  }
+}
+
+// out[i] = sum_j coeff[j] * poly_j[i - shift_j]
+template <class FrP>
+struct LincombArgs {
+  const Fp<FrP>* poly[kMaxLincomb];
+  size_t len[kMaxLincomb];
+  size_t shift[kMaxLincomb];
+  Fp<FrP> coeff[kMaxLincomb];
+  int k;
+};
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_poly_lincomb(const LincombArgs<FrP>* __restrict__ a, Fp<FrP>* __restrict__ out, size_t out_len) {
+  using Fr = Fp<FrP>;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < out_len; i += (size_t)gridDim.x * blockDim.x) {
+    Fr acc = Fr::zero();
+    for (int j = 0; j < a->k; j++) {
+      size_t sh = a->shift[j];
+      if (i >= sh && i - sh < a->len[j]) acc = Fr::add(acc, Fr::mul(a->coeff[j], ld_vec(&a->poly[j][i - sh])));
+    }
+    st_vec(&out[i], acc);
+  }
+}
+
+// batch inversion, one chunk of 64 per thread (Montgomery's trick, zeros are left untouched like
+// ark_ff::batch_inversion); prefix products go through `scratch`
+template <class FrP>
+__global__ void __launch_bounds__(128)
+k_batch_inverse(const Fp<FrP>* __restrict__ in, Fp<FrP>* __restrict__ out, Fp<FrP>* __restrict__ scratch, size_t n) {
+  using Fr = Fp<FrP>;
+  size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = c * kPolyChunk;
+  if (lo >= n) return;
+  size_t hi = lo + kPolyChunk < n ? lo + kPolyChunk : n;
+  Fr acc = Fr::one();
+  for (size_t j = lo; j < hi; j++) {
+    Fr v = ld_vec(&in[j]);
+    if (!v.is_zero()) acc = Fr::mul(acc, v);
+    st_vec(&scratch[j], acc);
+  }
+  Fr inv = Fr::inv(acc);
+  for (size_t j = hi; j-- > lo;) {
+    Fr v = ld_vec(&in[j]);
+    if (v.is_zero()) { st_vec(&out[j], v); continue; }
+    Fr prev = j > lo ? ld_vec_rw(&scratch[j - 1]) : Fr::one();
+    st_vec(&out[j], Fr::mul(inv, prev));
+    inv = Fr::mul(inv, v);
+  }
+}
+
+template <class FrP>
+static int div_linear_t(zkb_ctx* ctx, cudaStream_t st, const void* d_p_v, size_t n, const uint64_t* z_host, void* d_q_v,
+                        void* d_rem_v) {
+  using Fr = Fp<FrP>;
+  const Fr* d_p = (const Fr*)d_p_v;
+  Fr* d_q = (Fr*)d_q_v;
+  Fr* d_rem = (Fr*)d_rem_v;
+  if (n == 0) {
+    ZKB_CUDA(ctx, cudaMemsetAsync(d_rem, 0, sizeof(Fr), st));
+    return ZKB_OK;
+  }
+  Fr z;
+  memcpy(z.v, z_host, 32);
+  Scratch ws(ctx, st);
+  size_t sizes[kMaxLevels + 1];
+  int levels = 0;
+  sizes[0] = n;
+  while (sizes[levels] > 1 && levels < kMaxLevels) {
+    sizes[levels + 1] = (sizes[levels] + kPolyChunk - 1) / kPolyChunk;
+    levels++;
+  }
+  if (levels == 0) levels = 1, sizes[1] = 1;      // n == 1: one chunk
+  Fr* zp;
+  ZKB_TRY(ws.alloc(&zp, kMaxLevels));
+  ZKB_LAUNCH(ctx, (k_poly_zpows<FrP>), 1, 32, 0, st, z, levels, zp);
+  // up[l] = collapsed values feeding level l (up[0] = p); H[l] = suffix values of level l (l >= 1)
+  const Fr* up[kMaxLevels + 1];
+  Fr* Hs[kMaxLevels + 1];
+  up[0] = d_p;
+  for (int l = 1; l <= levels; l++) {
+    Fr* buf;
+    ZKB_TRY(ws.alloc(&buf, sizes[l]));
+    ZKB_LAUNCH(ctx, (k_poly_up<FrP>), ceil_div(sizes[l], 128), 128, 0, st, up[l - 1], sizes[l - 1], zp + (l - 1), buf, sizes[l]);
+    up[l] = buf;
+    ZKB_TRY(ws.alloc(&Hs[l], sizes[l]));
+  }
+  // downward: level `levels - 1` has a single chunk feeding from nothing, ..., level 0 writes q / rem
+  for (int l = levels - 1; l >= 0; l--) {
+    const Fr* upper = (l + 1 <= levels - 1) ? Hs[l + 1] : nullptr;     // suffix values of the chunks of level l
+    ZKB_LAUNCH(ctx, (k_poly_down<FrP>), ceil_div(sizes[l + 1], 128), 128, 0, st, up[l], sizes[l], zp + l, upper, sizes[l + 1],
+               l ? Hs[l] : (Fr*)nullptr, l == 0 ? 1 : 0, d_q, d_rem);
+  }
+  return ZKB_OK;
+}
+
+int poly_div_linear_dev(zkb_ctx* ctx, cudaStream_t st, int curve, const void* d_p, size_t n, const uint64_t* z_mont,
+                        void* d_q, void* d_rem) {
+  return curve == ZKB_BLS12_381 ? div_linear_t<BlsFr>(ctx, st, d_p, n, z_mont, d_q, d_rem)
+                                : div_linear_t<BnFr>(ctx, st, d_p, n, z_mont, d_q, d_rem);
+}
+
+template <class FrP>
+static int lincomb_t(zkb_ctx* ctx, cudaStream_t st, size_t k, const uint64_t* const* polys, const size_t* lens,
+                     const size_t* shifts, const uint64_t* coeffs, uint64_t* out, size_t out_len) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  LincombArgs<FrP> h;
+  memset(&h, 0, sizeof h);
+  h.k = (int)k;
+  for (size_t j = 0; j < k; j++) {
+    Fr* d;
+    ZKB_TRY(ws.alloc(&d, lens[j]));
+    if (lens[j]) ZKB_CUDA(ctx, cudaMemcpyAsync(d, polys[j], lens[j] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    h.poly[j] = d;
+    h.len[j] = lens[j];
+    h.shift[j] = shifts ? shifts[j] : 0;
+    memcpy(h.coeff[j].v, coeffs + 4 * j, 32);
+  }
+  LincombArgs<FrP>* d_args;
+  Fr* d_out;
+  ZKB_TRY(ws.alloc(&d_args, 1));
+  ZKB_TRY(ws.alloc(&d_out, out_len));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_args, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  unsigned blocks = ceil_div(out_len, 256);
+  if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  ZKB_LAUNCH(ctx, (k_poly_lincomb<FrP>), blocks, 256, 0, st, (const LincombArgs<FrP>*)d_args, d_out, out_len);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_len * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));      // h lives on this stack frame
+  return ZKB_OK;
+}
+
+template <class FrP>
+static int batch_inverse_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, uint64_t* out, size_t n) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  Fr *d_in, *d_out, *d_scr;
+  ZKB_TRY(ws.alloc(&d_in, n));
+  ZKB_TRY(ws.alloc(&d_out, n));
+  ZKB_TRY(ws.alloc(&d_scr, n));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  ZKB_LAUNCH(ctx, (k_batch_inverse<FrP>), ceil_div(ceil_div(n, kPolyChunk), 128), 128, 0, st, (const Fr*)d_in, d_out, d_scr, n);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+}  // namespace zkb
+
+using namespace zkb;
+
+extern "C" {
+
+int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t n, const uint64_t z_mont[4], uint64_t* q_mont,
+                        uint64_t rem_mont[4]) {
+  if (!ctx || (n && !p_mont) || !z_mont || !rem_mont) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "poly_div_linear: unknown curve %d", curve);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint32_t *d_p, *d_q, *d_rem;
+  ZKB_TRY(ws.alloc(&d_p, n * 8));
+  ZKB_TRY(ws.alloc(&d_q, n * 8));
+  ZKB_TRY(ws.alloc(&d_rem, 8));
+  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(d_p, p_mont, n * 32, cudaMemcpyHostToDevice, st));
+  ZKB_TRY(poly_div_linear_dev(ctx, st, curve, d_p, n, z_mont, q_mont ? d_q : nullptr, d_rem));
+  if (q_mont && n > 1) ZKB_CUDA(ctx, cudaMemcpyAsync(q_mont, d_q, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(rem_mont, d_rem, 32, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,
+                     const size_t* shifts, const uint64_t* coeffs_mont, uint64_t* out_mont, size_t out_len) {
+  if (!ctx || (k && (!polys_mont || !lens || !coeffs_mont)) || (out_len && !out_mont)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "poly_lincomb: unknown curve %d", curve);
+  if (k > (size_t)kMaxLincomb) return set_err(ctx, ZKB_E_INVALID, "poly_lincomb: at most %d polynomials", kMaxLincomb);
+  if (out_len == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? lincomb_t<BlsFr>(ctx, ctx->main, k, polys_mont, lens, shifts, coeffs_mont, out_mont, out_len)
+                                : lincomb_t<BnFr>(ctx, ctx->main, k, polys_mont, lens, shifts, coeffs_mont, out_mont, out_len);
+}
+
+int zkb_fr_batch_inverse(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n) {
+  if (!ctx || (n && (!in_mont || !out_mont))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "batch_inverse: unknown curve %d", curve);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? batch_inverse_t<BlsFr>(ctx, ctx->main, in_mont, out_mont, n)
+                                : batch_inverse_t<BnFr>(ctx, ctx->main, in_mont, out_mont, n);
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""The prover side of the reference's KZG10 polynomial commitment (`zkp_marlin::pc`) on the B200
+backend: same structure, argument meaning and error behaviour as
+
+    KZG10::commit / KZG10::open          marlin/src/pc/kzg10.rs:100-156
+    PC::commit / PC::open / batch_open   marlin/src/pc/mod.rs:34-160
+    CommitterKey, LabeledPolynomial, Randomness   marlin/src/pc/data_structures.rs:59-100,146-263
+
+The committer key lives in HBM (`powers_of_g`, `powers_of_gamma_g` uploaded once); commitments and
+opening witnesses are MSMs over it (zkb_msm_mont: Montgomery coefficients in, `into_repr` fused), the
+witness polynomial p / (x - z), the opening linear combination and the evaluations run on the GPU too.
+Polynomials are uint64[n, 4] Montgomery coefficient arrays, low degree first.
+"""
+import numpy as np
+
+from . import _lib
+from .backend import point_words
+from .r1cs import ints_to_limbs
+
+FR_MODULUS = {
+    _lib.BLS12_381: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+    _lib.BN254: 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
+}
+
+
+class KzgError(Exception):
+    """marlin/src/pc/error.rs"""
+
+
+class DegreeIsZero(KzgError):
+    pass
+
+
+class DegreeOutOfBound(KzgError):
+    pass
+
+
+class HidingBoundIsZero(KzgError):
+    pass
+
+
+class HidingBoundTooLarge(KzgError):
+    pass
+
+
+class MissingRng(KzgError):
+    pass
+
+
+class MissingPolynomial(KzgError):
+    pass
+
+
+def _degree(p):
+    nz = np.flatnonzero(p.any(axis=1))
+    return int(nz[-1]) if len(nz) else 0
+
+
+def _leading_zeros(p):
+    nz = np.flatnonzero(p.any(axis=1))
+    return int(nz[0]) if len(nz) else len(p)
+
+
+class CommitterKey:
+    """data_structures.rs:59-100 resident on one GPU."""
+
+    def __init__(self, ctx, curve, powers_of_g, powers_of_gamma_g, supported_degree=None):
+        """powers_*: (xy uint64[n, words], inf uint8[n]) in the layout of include/zkb.h"""
+        self.ctx, self.curve = ctx, curve
+        self.n = len(powers_of_g[1])
+        self.supported_degree = self.n - 1 if supported_degree is None else supported_degree
+        self.g = ctx.srs_upload(curve, _lib.G1, powers_of_g[0], powers_of_g[1])
+        self.gamma_g = ctx.srs_upload(curve, _lib.G1, powers_of_gamma_g[0], powers_of_gamma_g[1])
+        self.to_mont = lambda ints: ctx.fr_convert(curve, ints_to_limbs(ints), to_mont=True)
+
+    def free(self):
+        self.g.free()
+        self.gamma_g.free()
+
+
+class Randomness:
+    """kzg10 `Rand` (data_structures.rs:146-200): the blinding polynomial, empty = not hiding"""
+
+    def __init__(self, blinding=None):
+        self.blinding = np.zeros((0, 4), dtype=np.uint64) if blinding is None else blinding
+
+    def is_hiding(self):
+        return bool(self.blinding.any())
+
+    @staticmethod
+    def rand(ck, hiding_bound, rng):
+        """DensePolynomial::rand(hiding_bound, rng): hiding_bound + 1 coefficients, drawn in order"""
+        p = FR_MODULUS[ck.curve]
+        return Randomness(ck.to_mont([rng.randrange(p) for _ in range(hiding_bound + 1)]))
+
+
+class LabeledPolynomial:
+    """data_structures.rs:218-263"""
+
+    def __init__(self, label, coeffs_mont, degree_bound=None, hiding_bound=None):
+        self.label, self.coeffs = label, np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4)
+        self.degree_bound, self.hiding_bound = degree_bound, hiding_bound
+
+
+def _add_points(ctx, curve, pts):
+    """sum of a few affine points on the device (unit-scalar MSM over a throw-away SRS)"""
+    xy = np.stack([p[0] for p in pts])
+    inf = np.array([1 if p[1] else 0 for p in pts], dtype=np.uint8)
+    srs = ctx.srs_upload(curve, _lib.G1, xy, inf, precompute=False)
+    try:
+        ones = np.zeros((len(pts), 4), dtype=np.uint64)
+        ones[:, 0] = 1
+        return ctx.msm(srs, ones)
+    finally:
+        srs.free()
+
+
+def kzg_commit(ck, p, hiding_bound=None, rng=None, base_offset=0, supported_degree=None):
+    """KZG10::commit (kzg10.rs:100-123) over powers_of_g[base_offset..] -> ((xy, is_identity), Randomness)"""
+    ctx = ck.ctx
+    sup = (ck.n - 1 - base_offset) if supported_degree is None else supported_degree
+    deg = _degree(p)
+    if deg < 1:
+        raise DegreeIsZero()
+    if deg > sup:
+        raise DegreeOutOfBound()
+    nz = _leading_zeros(p)                                       # skip_leading_zeros_and_convert_to_bigints
+    comm = ctx.msm(ck.g, p[nz:], base_offset=base_offset + nz, mont=True)
+    rand = Randomness()
+    if hiding_bound is not None:
+        if rng is None:
+            raise MissingRng()
+        if hiding_bound == 0:
+            raise HidingBoundIsZero()
+        if hiding_bound > ck.n - base_offset:
+            raise HidingBoundTooLarge()
+        rand = Randomness.rand(ck, hiding_bound, rng)
+        rc = ctx.msm(ck.gamma_g, rand.blinding, mont=True)
+        comm = _add_points(ctx, ck.curve, [comm, rc])
+    return comm, rand
+
+
+def kzg_open(ck, p, point_mont, rand):
+    """KZG10::open (kzg10.rs:125-156) -> ((w xy, is_identity), rand_v Montgomery or None)"""
+    ctx = ck.ctx
+    deg = _degree(p)
+    if deg < 1:
+        raise DegreeIsZero()
+    if deg > ck.n:
+        raise DegreeOutOfBound()
+    witness, _ = ctx.poly_div_linear(ck.curve, p, point_mont)    # compute_witness_polynomial :211-226
+    nz = _leading_zeros(witness)
+    w = ctx.msm(ck.g, witness[nz:], base_offset=nz, mont=True)
+    rand_v = None
+    if rand.is_hiding():
+        rq, rand_v = ctx.poly_div_linear(ck.curve, rand.blinding, point_mont)
+        w = _add_points(ctx, ck.curve, [w, ctx.msm(ck.gamma_g, rq, mont=True)])
+    return w, rand_v
+
+
+def pc_commit(ck, polynomials, rng=None):
+    """PC::commit (pc/mod.rs:34-71) -> ([(comm, shifted_comm or None)], [(rand, shifted_rand or None)])"""
+    comms, rands = [], []
+    for P in polynomials:
+        comm, rand = kzg_commit(ck, P.coeffs, P.hiding_bound, rng, supported_degree=ck.supported_degree)
+        shifted, shifted_rand = None, None
+        if P.degree_bound is not None:
+            if P.degree_bound > ck.supported_degree:
+                raise DegreeOutOfBound()
+            off = ck.supported_degree - P.degree_bound              # shifted_powers (data_structures.rs:87-99)
+            shifted, shifted_rand = kzg_commit(ck, P.coeffs, P.hiding_bound, rng, base_offset=off,
+                                               supported_degree=P.degree_bound)
+        comms.append((comm, shifted))
+        rands.append((rand, shifted_rand))
+    return comms, rands
+
+
+def pc_open(ck, polynomials, point_mont, opening_challenge, randomnesses):
+    """PC::open (pc/mod.rs:73-100); opening_challenge is a canonical int"""
+    ctx = ck.ctx
+    mod = FR_MODULUS[ck.curve]
+    polys, shifts, coeffs = [], [], []
+    rpolys, rcoeffs = [], []
+    challenge = 1
+    for P, (rand, shifted_rand) in zip(polynomials, randomnesses):
+        polys.append(P.coeffs); shifts.append(0); coeffs.append(challenge)
+        if len(rand.blinding):
+            rpolys.append(rand.blinding); rcoeffs.append(challenge)
+        if P.degree_bound is not None:
+            sc = challenge * opening_challenge % mod
+            if P.coeffs.any():                                       # shift_polynomial (:241-250)
+                polys.append(P.coeffs); shifts.append(ck.supported_degree - P.degree_bound); coeffs.append(sc)
+            if shifted_rand is not None and len(shifted_rand.blinding):
+                rpolys.append(shifted_rand.blinding); rcoeffs.append(sc)
+        challenge = challenge * opening_challenge % mod * opening_challenge % mod
+    p = ctx.poly_lincomb(ck.curve, polys, ck.to_mont(coeffs), shifts)
+    r = Randomness(ctx.poly_lincomb(ck.curve, rpolys, ck.to_mont(rcoeffs)) if rpolys else None)
+    return kzg_open(ck, p, point_mont, r)
+
+
+def pc_batch_open(ck, polynomials, query_set, opening_challenge, randomnesses):
+    """PC::batch_open (pc/mod.rs:122-160).  query_set: iterable of (label, point canonical int); proofs are
+    returned in increasing order of the point (BTreeMap order), labels sorted inside a point."""
+    by_label = {P.label: (P, r) for P, r in zip(polynomials, randomnesses)}
+    point_to_labels = {}
+    for label, point in query_set:
+        point_to_labels.setdefault(point, set()).add(label)
+    proofs = []
+    for point in sorted(point_to_labels):
+        polys, rands = [], []
+        for label in sorted(point_to_labels[point]):
+            if label not in by_label:
+                raise MissingPolynomial(label)
+            polys.append(by_label[label][0])
+            rands.append(by_label[label][1])
+        proofs.append(pc_open(ck, polys, ck.to_mont([point])[0], opening_challenge, rands))
+    return proofs

@@ -158,6 +158,19 @@ int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_
 /* out[i] = into_repr(in[i]) (mode 0) or from_repr(in[i]) (mode 1) */
 int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode);
 
+/* ---- polynomial helpers of the Marlin prover (all Fr data Montgomery, host buffers) ----------
+ * q = p / (x - z) and rem = p(z): KZG10::compute_witness_polynomial (marlin/src/pc/kzg10.rs:211-226)
+ * and LabeledPolynomial::evaluate (marlin/src/lib.rs:147-156).  p has n coefficients (low degree
+ * first), q receives n - 1 (may be NULL to evaluate only). */
+int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t n, const uint64_t z_mont[4],
+                        uint64_t* q_mont, uint64_t rem_mont[4]);
+/* out[i] = sum_j coeffs[j] * polys[j][i - shifts[j]], i < out_len: the accumulation of PC::open
+ * (marlin/src/pc/mod.rs:85-98; shift = supported_degree - degree_bound, :241-250).  k <= 64. */
+int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,
+                     const size_t* shifts, const uint64_t* coeffs_mont, uint64_t* out_mont, size_t out_len);
+/* ark_ff::batch_inversion (marlin/src/ahp/prover.rs:365-367): out[i] = 1 / in[i], zeros stay zero. */
+int zkb_fr_batch_inverse(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n);
+
 /* ---- diagnostics: single field / group operations of the device arithmetic on n operands, used by
  * the parity tests to check the GPU arithmetic against the CPU oracle in isolation.
  * field: 0 BN254 Fr, 1 BLS12-381 Fr, 2 BN254 Fq, 3 BLS12-381 Fq.

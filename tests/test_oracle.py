@@ -102,3 +102,33 @@ def test_golden_groth16(name, cid, build):
     # r = 0 guard (prover.rs:170) and s = 0
     for rr, ss in ((0, 5), (5, 0), (0, 0)):
         assert OG.create_proof(pk, cs, rr, ss) == OG.proof_in_exponent(pk, cs, rr, ss)
+
+
+def test_kzg10_oracle_self_consistency():
+    """oracle/pyref/kzg10.py: commitments and opening witnesses equal the trapdoor-side exponent
+    formula, and the restated KZG10::check accepts / rejects (marlin/src/pc/kzg10.rs:158-172)."""
+    from oracle.pyref import kzg10 as K
+    cid = BLS12_381
+    mod = FR[cid].p
+    rng = random.Random(1)
+    pp = K.setup(cid, 10, rng.randrange(mod), g_scalar=rng.randrange(1, mod), gamma=rng.randrange(1, mod))
+    ck = K.trim(pp, 6)
+    p = [0, rng.randrange(mod), 0, rng.randrange(mod), rng.randrange(mod)]
+    bl = [rng.randrange(mod), rng.randrange(mod)]
+    c = K.kzg_commit(cid, ck["powers_of_g"], ck["powers_of_gamma_g"], p, bl, 6)
+    ce = K.commitment_exponent(ck, p, bl)
+    assert c == K.exponent_point(ck, ce)
+    z = rng.randrange(mod)
+    w, rv = K.kzg_open(cid, ck["powers_of_g"], ck["powers_of_gamma_g"], p, z, bl)
+    we = K.commitment_exponent(ck, K.poly_div_linear(p, z, mod), K.poly_div_linear(bl, z, mod))
+    assert w == K.exponent_point(ck, we)
+    assert K.kzg_check_in_exponent(ck, ce, z, K.poly_eval(p, z, mod), we, rv)
+    assert not K.kzg_check_in_exponent(ck, ce, z, (K.poly_eval(p, z, mod) + 1) % mod, we, rv)
+    q = K.poly_div_linear(p, z, mod)
+    x = rng.randrange(mod)
+    assert ((x - z) * K.poly_eval(q, x, mod) + K.poly_eval(p, z, mod)) % mod == K.poly_eval(p, x, mod)
+    with pytest.raises(K.KzgError):
+        K.kzg_commit(cid, ck["powers_of_g"], ck["powers_of_gamma_g"], [5], None, 6)
+    # degree-bounded polynomial: shifted commitment exponent carries beta^(supported - bound)
+    out = K.pc_commit(ck, [{"coeffs": p, "degree_bound": 4, "blinding": bl, "shifted_blinding": bl}])
+    assert out[0][1] == K.exponent_point(ck, K.commitment_exponent(ck, p, bl, shift=2))
