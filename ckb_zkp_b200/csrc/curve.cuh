@@ -27,7 +27,7 @@ struct Affine {
 template <class F> struct XYZZ;
 template <class F> ZKB_NOINLINE void pt_add(XYZZ<F>& a, const XYZZ<F>& b);
 template <class F> ZKB_NOINLINE void pt_dbl(XYZZ<F>& a);
-template <class F> ZKB_NOINLINE void pt_dbl_affine(XYZZ<F>& out, const F& x, const F& y);
+template <class F> ZKB_NOINLINE XYZZ<F> pt_dbl_affine(F x, F y);
 template <class F> ZKB_NOINLINE void pt_madd(XYZZ<F>& a, const Affine<F>& p, bool negate);
 template <class F> ZKB_NOINLINE void pt_to_affine(Affine<F>& out, const XYZZ<F>& a);
 
@@ -86,7 +86,7 @@ struct XYZZ {
     F Pp = F::sub(U2, X);
     F R = F::sub(S2, Y);
     if (Pp.is_zero()) {
-      if (R.is_zero()) pt_dbl_affine(*this, x2, y2);
+      if (R.is_zero()) *this = pt_dbl_affine<F>(x2, y2);
       else *this = inf();
       return;
     }
@@ -157,8 +157,13 @@ struct XYZZ {
 
 template <class F> ZKB_NOINLINE void pt_add(XYZZ<F>& a, const XYZZ<F>& b) { a.add(b); }
 template <class F> ZKB_NOINLINE void pt_dbl(XYZZ<F>& a) { a = XYZZ<F>::dbl(a); }
-template <class F> ZKB_NOINLINE void pt_dbl_affine(XYZZ<F>& out, const F& x, const F& y) { out = XYZZ<F>::dbl_affine(x, y); }
+template <class F> ZKB_NOINLINE XYZZ<F> pt_dbl_affine(F x, F y) { return XYZZ<F>::dbl_affine(x, y); }
 template <class F> ZKB_NOINLINE void pt_madd(XYZZ<F>& a, const Affine<F>& p, bool negate) { a.madd(p, negate); }
 template <class F> ZKB_NOINLINE void pt_to_affine(Affine<F>& out, const XYZZ<F>& a) { out = a.to_affine(); }
+
+// the call-multiplication twin of a coordinate field (same memory layout)
+template <class F> struct CallVariant;
+template <class P> struct CallVariant<Fp<P>> { using type = FpC<P>; };
+template <class P> struct CallVariant<Fp2<P, Fp<P>>> { using type = Fp2<P, FpC<P>>; };
 
 }  // namespace zkb

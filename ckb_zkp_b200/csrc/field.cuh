@@ -207,9 +207,43 @@ struct alignas(16) Fp {
 // ---------------------------------------------------------------------------------
 // Fq2 = Fq[u]/(u^2+1)   (ark-ff `Fp2` with NONRESIDUE = -1 for both curves)
 // ---------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------
+// FpC: the same field element (same bytes) whose multiplication is an out-of-line call.
+// The bucket-accumulation loop is instruction-fetch bound when ten fully unrolled 381-bit
+// multiplications are inlined (46 KB of SASS per iteration); with the multiplication as one
+// shared 4.6 KB function the loop body fits the instruction cache.  Operands travel in
+// registers (by-value ABI), the extra MOVs issue in the slots the 4-cycle IMAD.WIDE leaves free.
+// ---------------------------------------------------------------------------------
+#ifdef __CUDACC__
 template <class P>
+__device__ __noinline__ Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) { return Fp<P>::mul(a, b); }
+#else
+template <class P>
+inline Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) { return Fp<P>::mul(a, b); }
+#endif
+
+template <class P>
+struct alignas(16) FpC {
+  static constexpr int N = P::N;
+  using Params = P;
+  Fp<P> f;
+  ZKB_HD static FpC zero() { return {Fp<P>::zero()}; }
+  ZKB_HD static FpC one() { return {Fp<P>::one()}; }
+  ZKB_HD bool is_zero() const { return f.is_zero(); }
+  ZKB_HD bool operator==(const FpC& o) const { return f == o.f; }
+  ZKB_HD bool operator!=(const FpC& o) const { return f != o.f; }
+  ZKB_HD static FpC add(const FpC& a, const FpC& b) { return {Fp<P>::add(a.f, b.f)}; }
+  ZKB_HD static FpC sub(const FpC& a, const FpC& b) { return {Fp<P>::sub(a.f, b.f)}; }
+  ZKB_HD static FpC neg(const FpC& a) { return {Fp<P>::neg(a.f)}; }
+  ZKB_HD static FpC dbl(const FpC& a) { return {Fp<P>::dbl(a.f)}; }
+  ZKB_HD static FpC mul(const FpC& a, const FpC& b) { return {fp_mul_call<P>(a.f, b.f)}; }
+  ZKB_HD static FpC sqr(const FpC& a) { return {fp_mul_call<P>(a.f, a.f)}; }
+  ZKB_HD static FpC inv(const FpC& a) { return {Fp<P>::inv(a.f)}; }
+};
+
+template <class P, class BaseT = Fp<P>>
 struct Fp2 {
-  using Base = Fp<P>;
+  using Base = BaseT;
   using Params = P;
   Base c0, c1;
 

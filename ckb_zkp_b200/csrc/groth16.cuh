@@ -37,10 +37,13 @@ struct Groth16Stage {
   void* results = nullptr;   // device block holding MSM results and the proof (layout in groth16_impl.cuh)
   void* scal = nullptr;      // device Fr[4]: r, s, r*s (canonical), spare
   bool staged = false;
+  // matrices whose upload is deferred into prove_staged (host pointers, valid for the duration of zkb_groth16_prove)
+  const zkb_csr* pending[3] = {nullptr, nullptr, nullptr};
 };
 
 struct Groth16Ops {
-  int (*stage)(zkb_ctx*, const zkb_pk*, const zkb_csr*, const zkb_csr*, const zkb_csr*, const uint64_t*, size_t, size_t);
+  int (*stage)(zkb_ctx*, const zkb_pk*, const zkb_csr*, const zkb_csr*, const zkb_csr*, const uint64_t*, size_t, size_t,
+               int defer_matrices);
   int (*compute_h)(zkb_ctx*, cudaStream_t);        // staged inputs -> h (canonical) in stage->va
   int (*prove_staged)(zkb_ctx*, const zkb_pk*, const uint64_t*, const uint64_t*);
   int (*fetch_proof)(zkb_ctx*, const zkb_pk*, uint64_t*, uint8_t*);

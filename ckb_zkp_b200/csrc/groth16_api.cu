@@ -94,7 +94,7 @@ int zkb_groth16_stage(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zk
   if (!ctx || !pk) return ZKB_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  return groth16_ops(pk->curve)->stage(ctx, pk, A, B, C, z_mont, n_inputs, n_aux);
+  return groth16_ops(pk->curve)->stage(ctx, pk, A, B, C, z_mont, n_inputs, n_aux, 0);
 }
 
 int zkb_groth16_prove_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t r[4], const uint64_t s[4]) {
@@ -118,7 +118,7 @@ int zkb_groth16_prove(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zk
   std::lock_guard<std::mutex> lk(ctx->mu);
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   const Groth16Ops* ops = groth16_ops(pk->curve);
-  ZKB_TRY(ops->stage(ctx, pk, A, B, C, z_mont, n_inputs, n_aux));
+  ZKB_TRY(ops->stage(ctx, pk, A, B, C, z_mont, n_inputs, n_aux, 1));
   ZKB_TRY(ops->prove_staged(ctx, pk, r, s));
   return ops->fetch_proof(ctx, pk, proof_xy, proof_inf);
 }
@@ -130,7 +130,7 @@ int zkb_groth16_h(zkb_ctx* ctx, int curve, const zkb_csr* A, const zkb_csr* B, c
   const Groth16Ops* ops = groth16_ops(curve);
   if (!ops) return set_err(ctx, ZKB_E_INVALID, "groth16_h: unknown curve %d", curve);
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
-  ZKB_TRY(ops->stage(ctx, nullptr, A, B, C, z_mont, n_inputs, n_aux));
+  ZKB_TRY(ops->stage(ctx, nullptr, A, B, C, z_mont, n_inputs, n_aux, 0));
   ZKB_TRY(ops->compute_h(ctx, ctx->main));
   return ops->fetch_h(ctx, h_canonical);
 }

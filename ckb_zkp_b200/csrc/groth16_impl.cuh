@@ -214,8 +214,10 @@ struct Groth16Impl {
     return ZKB_OK;
   }
 
+  // defer_matrices: copy only the assignment now; prove_staged uploads A, B, C after it has started the
+  // four assignment MSMs on their side streams, so the 200 MB of matrix traffic overlaps their compute
   static int stage(zkb_ctx* ctx, const zkb_pk*, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
-                   const uint64_t* z_mont, size_t n_inputs, size_t n_aux) {
+                   const uint64_t* z_mont, size_t n_inputs, size_t n_aux, int defer_matrices) {
     if (!ctx->stage) ctx->stage = new Groth16Stage();
     Groth16Stage* s = ctx->stage;
     s->staged = false;
@@ -242,9 +244,17 @@ struct Groth16Impl {
     if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, sizeof(Res)));
     if (!s->scal) ZKB_CUDA(ctx, cudaMalloc(&s->scal, sizeof(Fr) * 4));
     ZKB_CUDA(ctx, cudaMemcpyAsync(s->z.p, z_mont, nz * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    ZKB_TRY(upload_csr(ctx, st, &s->A, A));
-    ZKB_TRY(upload_csr(ctx, st, &s->B, B));
-    ZKB_TRY(upload_csr(ctx, st, &s->C, C));
+    s->pending[0] = s->pending[1] = s->pending[2] = nullptr;
+    if (defer_matrices) {
+      for (const zkb_csr* m : {A, B, C})
+        if ((m->n_rows && !m->row_ptr) || (m->nnz && (!m->col_idx || !m->coeff_mont)))
+          return set_err(ctx, ZKB_E_INVALID, "groth16: null matrix");
+      s->pending[0] = A; s->pending[1] = B; s->pending[2] = C;
+    } else {
+      ZKB_TRY(upload_csr(ctx, st, &s->A, A));
+      ZKB_TRY(upload_csr(ctx, st, &s->B, B));
+      ZKB_TRY(upload_csr(ctx, st, &s->C, C));
+    }
     s->staged = true;
     return ZKB_OK;
   }
@@ -317,6 +327,12 @@ struct Groth16Impl {
     ZKB_TRY(g1->msm_run(ctx, ctx->side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
     ZKB_TRY(g1->msm_run(ctx, ctx->side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
     ZKB_TRY(g1->msm_run(ctx, ctx->side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
+    if (s->pending[0]) {
+      ZKB_TRY(upload_csr(ctx, st, &s->A, s->pending[0]));
+      ZKB_TRY(upload_csr(ctx, st, &s->B, s->pending[1]));
+      ZKB_TRY(upload_csr(ctx, st, &s->C, s->pending[2]));
+      s->pending[0] = s->pending[1] = s->pending[2] = nullptr;
+    }
     ZKB_TRY(compute_h(ctx, st));
     ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
     ZKB_TRY(join_streams(ctx, 5));

@@ -249,8 +249,8 @@ static __global__ void k_big_chunk_map(const uint32_t* __restrict__ offsets, con
 // bucket accumulation
 // ------------------------------------------------------------------------------------------
 // one thread per regular bucket, in order of decreasing size
-template <class F>
-__global__ void __launch_bounds__(128)
+template <class F, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
              const uint32_t* __restrict__ order, const MsmSched* __restrict__ sched,
              const Affine<F>* __restrict__ table, XYZZ<F>* __restrict__ bucket_acc) {
@@ -448,7 +448,8 @@ k_precompute(Affine<F>* table, uint32_t n, int c, int W) {
 // host orchestration
 // ------------------------------------------------------------------------------------------
 // Window width from a cost model in field multiplications: n * W mixed additions (10 mul) plus the
-// bucket reduction, ~2.3 full additions (14 mul) per bucket of every bucket set.
+// bucket reduction, ~2.3 full additions (14 mul) per bucket of every bucket set.  Checked against a
+// sweep of c on the 2^20-constraint proof (c = 16..22 -> 80, 53, 48, 47, 43, 49, 51 ms).
 inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
   if (n < 2) n = 2;
   int best_c = 4;
@@ -458,6 +459,10 @@ inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
     int W = msm_windows(scalar_bits, c);
     double sets = precomp ? 1.0 : (double)W;
     double cost = (double)n * W * 10.0 + sets * (double)(size_t(1) << (c - 1)) * 32.0;
+    // a narrow top window funnels its n entries into a few buckets, which then take the slower chunked
+    // path (measured: c = 19 loses to c = 20 at n = 2^19..2^20 although it has fewer buckets)
+    int top_bits = scalar_bits + 1 - c * (W - 1);
+    if (top_bits < c - 5) cost += (double)n * 20.0;
     if (!precomp) cost += (double)W * c * 9.0;      // doubling chain of the window combine (negligible)
     if (cost < best) { best = cost; best_c = c; }
   }
@@ -562,8 +567,23 @@ struct MsmEngine {
     ZKB_TRY(ws.alloc(&partial, max_chunks));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
     prof_begin(ctx, st);
-    ZKB_LAUNCH(ctx, (k_accumulate<F>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
-               (const Aff*)srs->table, bucket_acc);
+    {
+      using FC = typename CallVariant<F>::type;
+      static_assert(sizeof(Affine<FC>) == sizeof(Aff) && sizeof(XYZZ<FC>) == sizeof(Pt), "call variant layout");
+      // tuning switches (defaults chosen from measurements): multiplication as a call,
+      // and a register cap that trades a few spills for a fourth resident block per SM
+      static const int use_call = []() { const char* e = getenv("ZKB_ACC_CALL"); return e ? atoi(e) : 0; }();
+      static const int occ4 = []() { const char* e = getenv("ZKB_ACC_OCC4"); return e ? atoi(e) : 0; }();
+      if (use_call)
+        ZKB_LAUNCH(ctx, (k_accumulate<FC, 3>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+                   (const Affine<FC>*)srs->table, (XYZZ<FC>*)bucket_acc);
+      else if (occ4)
+        ZKB_LAUNCH(ctx, (k_accumulate<F, 4>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+                   (const Aff*)srs->table, bucket_acc);
+      else
+        ZKB_LAUNCH(ctx, (k_accumulate<F, 1>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+                   (const Aff*)srs->table, bucket_acc);
+    }
     prof_end(ctx, st, (double)n * (32.0 + sizeof(Aff)));   // one read of each (scalar, base) pair
     {
       // grids are upper bounds read against device-side counts (no host round trip)
