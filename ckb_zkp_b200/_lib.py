@@ -62,6 +62,9 @@ SIGNATURES = {
     "zkb_poly_div_linear": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zkb_poly_lincomb": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_fr_batch_inverse": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t]),
+    "zkb_fr_vec_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "zkb_fr_powers": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
+    "zkb_spmv": (c_int, [c_void_p, c_int, ctypes.POINTER(Csr), c_void_p, c_size_t, c_void_p]),
     "zkb_debug_fp_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_debug_pt_op": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t]),
 }

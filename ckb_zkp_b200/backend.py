@@ -232,6 +232,32 @@ class Context:
         self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, _ptr(a), _ptr(out), a.shape[0]))
         return out
 
+    VEC_ADD, VEC_SUB, VEC_MUL, VEC_SCALE, VEC_AXPY, VEC_RSUB, VEC_ADDC = range(7)
+
+    def fr_vec_op(self, curve, op, a, b=None, s=None):
+        """elementwise op on uint64[n, 4] Montgomery arrays (see zkb_fr_vec_op); s = uint64[4] scalar"""
+        a = _fr(a, "a")
+        b = None if b is None else _fr(b, "b")
+        if b is not None and b.shape != a.shape:
+            raise ValueError("operand shapes differ")
+        s = None if s is None else np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        out = np.zeros_like(a)
+        self._check(self.lib.zkb_fr_vec_op(self.handle, curve, op, _ptr(a), _ptr(b), _ptr(s), _ptr(out), a.shape[0]))
+        return out
+
+    def fr_powers(self, curve, base_mont, n, scale_mont=None):
+        base = np.ascontiguousarray(base_mont, dtype=np.uint64).reshape(4)
+        sc = None if scale_mont is None else np.ascontiguousarray(scale_mont, dtype=np.uint64).reshape(4)
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self._check(self.lib.zkb_fr_powers(self.handle, curve, _ptr(base), _ptr(sc), _ptr(out), n))
+        return out
+
+    def spmv(self, curve, m, x_mont):
+        x = _fr(x_mont, "x")
+        y = np.zeros((m.n_rows, 4), dtype=np.uint64)
+        self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), _ptr(x), x.shape[0], _ptr(y)))
+        return y
+
     # -- Groth16 ------------------------------------------------------------------------------
     def groth16_h(self, curve, A, B, C, z_mont, n_inputs, n_aux):
         z = _fr(z_mont, "assignment")

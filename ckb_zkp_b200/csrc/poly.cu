@@ -120,6 +120,120 @@ k_batch_inverse(const Fp<FrP>* __restrict__ in, Fp<FrP>* __restrict__ out, Fp<Fr
   }
 }
 
+// elementwise vector operations used by the AHP rounds (marlin/src/ahp/prover.rs pointwise loops)
+//   0: a + b   1: a - b   2: a * b   3: s * a   4: a + s * b   5: s - a   6: a + s
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_fr_vec_op(int op, const Fp<FrP>* __restrict__ a, const Fp<FrP>* __restrict__ b, Fp<FrP> s, Fp<FrP>* __restrict__ out, size_t n) {
+  using Fr = Fp<FrP>;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    Fr x = ld_vec(&a[i]);
+    Fr y = (op == 0 || op == 1 || op == 2 || op == 4) ? ld_vec(&b[i]) : Fr::zero();
+    Fr r;
+    switch (op) {
+      case 0: r = Fr::add(x, y); break;
+      case 1: r = Fr::sub(x, y); break;
+      case 2: r = Fr::mul(x, y); break;
+      case 3: r = Fr::mul(x, s); break;
+      case 4: r = Fr::add(x, Fr::mul(y, s)); break;
+      case 5: r = Fr::sub(s, x); break;
+      default: r = Fr::add(x, s); break;
+    }
+    st_vec(&out[i], r);
+  }
+}
+// out[i] = scale * base^i
+template <class FrP>
+__global__ void __launch_bounds__(128)
+k_fr_powers(Fp<FrP> base, Fp<FrP> scale, Fp<FrP>* __restrict__ out, size_t n) {
+  using Fr = Fp<FrP>;
+  constexpr int CH = 32;
+  size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * CH;
+  if (i0 >= n) return;
+  Fr cur = Fr::mul(Fr::pow_u64(base, (uint64_t)i0), scale);
+  for (int k = 0; k < CH && i0 + k < n; k++) {
+    st_vec(&out[i0 + k], cur);
+    cur = Fr::mul(cur, base);
+  }
+}
+// y[i] = sum_p coeff[p] * x[col[p]] over row i (generic sparse matrix-vector product)
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_spmv_generic(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx, const Fp<FrP>* __restrict__ coeff,
+               const Fp<FrP>* __restrict__ x, Fp<FrP>* __restrict__ y, uint32_t n_rows) {
+  using Fr = Fp<FrP>;
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  Fr acc = Fr::zero();
+  const Fr one = Fr::one();
+  for (uint32_t p = row_ptr[i]; p < row_ptr[i + 1]; p++) {
+    Fr c = ld_vec(&coeff[p]);
+    Fr v = ld_vec(&x[col_idx[p]]);
+    if (c != one) v = Fr::mul(v, c);
+    acc = Fr::add(acc, v);
+  }
+  st_vec(&y[i], acc);
+}
+
+template <class FrP>
+static int vec_op_t(zkb_ctx* ctx, cudaStream_t st, int op, const uint64_t* a, const uint64_t* b, const uint64_t* s_host,
+                    uint64_t* out, size_t n) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  Fr *d_a, *d_b, *d_o;
+  const bool binary = op == 0 || op == 1 || op == 2 || op == 4;
+  ZKB_TRY(ws.alloc(&d_a, n));
+  ZKB_TRY(ws.alloc(&d_b, binary ? n : 1));
+  ZKB_TRY(ws.alloc(&d_o, n));
+  Fr s = Fr::zero();
+  if (s_host) memcpy(s.v, s_host, 32);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  if (binary) ZKB_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+  ZKB_LAUNCH(ctx, (k_fr_vec_op<FrP>), blocks, 256, 0, st, op, (const Fr*)d_a, (const Fr*)d_b, s, d_o, n);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+template <class FrP>
+static int powers_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* base, const uint64_t* scale, uint64_t* out, size_t n) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  Fr* d_o;
+  ZKB_TRY(ws.alloc(&d_o, n));
+  Fr b, sc = Fr::one();
+  memcpy(b.v, base, 32);
+  if (scale) memcpy(sc.v, scale, 32);
+  ZKB_LAUNCH(ctx, (k_fr_powers<FrP>), ceil_div(ceil_div(n, 32), 128), 128, 0, st, b, sc, d_o, n);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+template <class FrP>
+static int spmv_t(zkb_ctx* ctx, cudaStream_t st, const zkb_csr* m, const uint64_t* x, size_t n_cols, uint64_t* y) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  uint32_t *d_ptr, *d_col;
+  Fr *d_coeff, *d_x, *d_y;
+  ZKB_TRY(ws.alloc(&d_ptr, m->n_rows + 1));
+  ZKB_TRY(ws.alloc(&d_col, m->nnz));
+  ZKB_TRY(ws.alloc(&d_coeff, m->nnz));
+  ZKB_TRY(ws.alloc(&d_x, n_cols));
+  ZKB_TRY(ws.alloc(&d_y, m->n_rows));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_ptr, m->row_ptr, (m->n_rows + 1) * 4, cudaMemcpyHostToDevice, st));
+  if (m->nnz) {
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_col, m->col_idx, m->nnz * 4, cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_coeff, m->coeff_mont, m->nnz * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  }
+  if (n_cols) ZKB_CUDA(ctx, cudaMemcpyAsync(d_x, x, n_cols * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  ZKB_LAUNCH(ctx, (k_spmv_generic<FrP>), ceil_div(m->n_rows, 256), 256, 0, st, (const uint32_t*)d_ptr, (const uint32_t*)d_col,
+             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (uint32_t)m->n_rows);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(y, d_y, m->n_rows * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 template <class FrP>
 static int div_linear_t(zkb_ctx* ctx, cudaStream_t st, const void* d_p_v, size_t n, const uint64_t* z_host, void* d_q_v,
                         void* d_rem_v) {
@@ -252,6 +366,42 @@ int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* p
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   return curve == ZKB_BLS12_381 ? lincomb_t<BlsFr>(ctx, ctx->main, k, polys_mont, lens, shifts, coeffs_mont, out_mont, out_len)
                                 : lincomb_t<BnFr>(ctx, ctx->main, k, polys_mont, lens, shifts, coeffs_mont, out_mont, out_len);
+}
+
+int zkb_fr_vec_op(zkb_ctx* ctx, int curve, int op, const uint64_t* a_mont, const uint64_t* b_mont, const uint64_t* s_mont,
+                  uint64_t* out_mont, size_t n) {
+  if (!ctx || op < 0 || op > 6 || (n && (!a_mont || !out_mont))) return ZKB_E_INVALID;
+  const bool binary = op == 0 || op == 1 || op == 2 || op == 4;
+  const bool scalar = op >= 3;
+  if (n && ((binary && !b_mont) || (scalar && !s_mont))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "fr_vec_op: unknown curve %d", curve);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? vec_op_t<BlsFr>(ctx, ctx->main, op, a_mont, b_mont, s_mont, out_mont, n)
+                                : vec_op_t<BnFr>(ctx, ctx->main, op, a_mont, b_mont, s_mont, out_mont, n);
+}
+
+int zkb_fr_powers(zkb_ctx* ctx, int curve, const uint64_t base_mont[4], const uint64_t* scale_mont, uint64_t* out_mont, size_t n) {
+  if (!ctx || !base_mont || (n && !out_mont)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "fr_powers: unknown curve %d", curve);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? powers_t<BlsFr>(ctx, ctx->main, base_mont, scale_mont, out_mont, n)
+                                : powers_t<BnFr>(ctx, ctx->main, base_mont, scale_mont, out_mont, n);
+}
+
+int zkb_spmv(zkb_ctx* ctx, int curve, const zkb_csr* m, const uint64_t* x_mont, size_t n_cols, uint64_t* y_mont) {
+  if (!ctx || !m || (m->n_rows && (!m->row_ptr || !y_mont)) || (m->nnz && (!m->col_idx || !m->coeff_mont || !x_mont)))
+    return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "spmv: unknown curve %d", curve);
+  if (m->n_rows == 0) return ZKB_OK;
+  if (m->n_rows >= (size_t(1) << 31) || m->nnz >= (size_t(1) << 32)) return set_err(ctx, ZKB_E_INVALID, "spmv: matrix too large");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? spmv_t<BlsFr>(ctx, ctx->main, m, x_mont, n_cols, y_mont)
+                                : spmv_t<BnFr>(ctx, ctx->main, m, x_mont, n_cols, y_mont);
 }
 
 int zkb_fr_batch_inverse(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n) {

@@ -1,0 +1,327 @@
+"""Marlin's AHP prover rounds (`zkp_marlin::ahp`, marlin/src/ahp/prover.rs:86-427) on the B200 backend.
+
+Same round structure, argument meaning and outputs as the reference:
+
+    prover_init          prover.rs:86-147     z_A = A z, z_B = B z (device SpMV)
+    prover_first_round   prover.rs:150-222    w, z_a, z_b, mask
+    prover_second_round  prover.rs:230-321    t, g_1, h_1
+    prover_third_round   prover.rs:331-427    g_2, h_2
+
+Every transform (interpolate / evaluate_over_domain = zkb_ntt), pointwise loop (zkb_fr_vec_op), batch
+inversion (zkb_fr_batch_inverse), sparse accumulation (zkb_spmv) and domain-element table (zkb_fr_powers)
+runs on the GPU; commitments and openings go through `kzg10.py`.  Data stays in host arrays between
+calls in this round of the build (one H2D/D2H per primitive) -- correct, not yet fast; keeping the round
+state resident is listed as next work in DESIGN.md.
+
+The index (indexer.rs:71-116) is an input, as in the reference where `index()` runs once per circuit;
+randomness and verifier challenges are explicit arguments (the Fiat-Shamir byte stream of
+marlin/src/fs_rng.rs is produced by the Rust host).  Polynomials are uint64[n, 4] Montgomery coefficient
+arrays, low degree first, trimmed like ark-poly's DensePolynomial.
+"""
+import numpy as np
+
+from . import _lib
+from .backend import CsrMatrix
+from .r1cs import ints_to_limbs
+
+FR_MODULUS = {
+    _lib.BLS12_381: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+    _lib.BN254: 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001,
+}
+FR_GENERATOR = {_lib.BLS12_381: 7, _lib.BN254: 5}
+FR_TWO_ADICITY = {_lib.BLS12_381: 32, _lib.BN254: 28}
+R = 1 << 256
+
+
+class PolynomialDegreeTooLarge(Exception):
+    """SynthesisError::PolynomialDegreeTooLarge (EvaluationDomain::new -> None)"""
+
+
+class InstanceDoesNotMatchIndex(Exception):
+    pass
+
+
+def domain_size(n):
+    """GeneralEvaluationDomain::compute_size_of_domain: next power of two"""
+    return 1 << max(n - 1, 0).bit_length()
+
+
+def reindex_by_subdomain(h_size, x_size, index):
+    """ark-poly EvaluationDomain::reindex_by_subdomain (vectorised over numpy index arrays)"""
+    index = np.asarray(index, dtype=np.int64)
+    period = h_size // x_size
+    i = index - x_size
+    return np.where(index < x_size, index * period, i + i // max(period - 1, 1) + 1)
+
+
+class Field:
+    """scalar-side helper: canonical ints <-> Montgomery limbs for a handful of values"""
+
+    def __init__(self, curve):
+        self.curve, self.p = curve, FR_MODULUS[curve]
+        self.rinv = pow(R, -1, self.p)
+
+    def mont(self, x):
+        return ints_to_limbs([x % self.p * R % self.p])[0]
+
+    def mont_arr(self, xs):
+        return ints_to_limbs([x % self.p * R % self.p for x in xs])
+
+    def to_int(self, limbs):
+        return int.from_bytes(np.ascontiguousarray(limbs, dtype=np.uint64).tobytes(), "little") * self.rinv % self.p
+
+    def root_of_unity(self, size):
+        log = size.bit_length() - 1
+        if log > FR_TWO_ADICITY[self.curve]:
+            raise PolynomialDegreeTooLarge()
+        w = pow(FR_GENERATOR[self.curve], (self.p - 1) >> FR_TWO_ADICITY[self.curve], self.p)
+        for _ in range(log, FR_TWO_ADICITY[self.curve]):
+            w = w * w % self.p
+        return w
+
+    def vanishing_at(self, size, x):
+        return (pow(x, size, self.p) - 1) % self.p
+
+
+def trim(p):
+    nz = np.flatnonzero(p.any(axis=1))
+    return p[:int(nz[-1]) + 1] if len(nz) else p[:0]
+
+
+def pad(p, n):
+    """a fresh array of exactly n coefficients (always a copy: the transforms work in place)"""
+    if len(p) >= n:
+        return p[:n].copy()
+    out = np.zeros((n, 4), dtype=np.uint64)
+    out[:len(p)] = p
+    return out
+
+
+class Ops:
+    """device-backed polynomial / vector arithmetic for one (ctx, curve)"""
+
+    def __init__(self, ctx, curve):
+        self.ctx, self.curve, self.f = ctx, curve, Field(curve)
+
+    def _v(self, op, a, b=None, s=None):
+        return self.ctx.fr_vec_op(self.curve, op, a, b, None if s is None else self.f.mont(s))
+
+    def add(self, a, b): return self._v(self.ctx.VEC_ADD, a, b)
+    def sub(self, a, b): return self._v(self.ctx.VEC_SUB, a, b)
+    def mul(self, a, b): return self._v(self.ctx.VEC_MUL, a, b)
+    def scale(self, a, s): return self._v(self.ctx.VEC_SCALE, a, s=s)
+    def axpy(self, a, s, b): return self._v(self.ctx.VEC_AXPY, a, b, s)          # a + s * b
+    def rsub(self, s, a): return self._v(self.ctx.VEC_RSUB, a, s=s)              # s - a
+    def addc(self, a, s): return self._v(self.ctx.VEC_ADDC, a, s=s)              # a + s
+    def inv(self, a): return self.ctx.fr_batch_inverse(self.curve, a)
+
+    def fft(self, coeffs, size):
+        """domain.fft(&coeffs): evaluations over the size-`size` domain"""
+        a = pad(coeffs, size)
+        return self.ctx.ntt(self.curve, a, size.bit_length() - 1)
+
+    def ifft(self, evals, size):
+        """Evaluations::interpolate"""
+        a = pad(evals, size)
+        return self.ctx.ntt(self.curve, a, size.bit_length() - 1, inverse=True)
+
+    def elements(self, size):
+        """domain.elements(): w^i"""
+        return self.ctx.fr_powers(self.curve, self.f.mont(self.f.root_of_unity(size)), size)
+
+    def poly_add(self, a, b):
+        n = max(len(a), len(b))
+        return trim(self.add(pad(a, n), pad(b, n))) if n else a[:0]
+
+    def poly_sub(self, a, b):
+        n = max(len(a), len(b))
+        return trim(self.sub(pad(a, n), pad(b, n))) if n else a[:0]
+
+    def poly_mul(self, a, b):
+        a, b = trim(a), trim(b)
+        if not len(a) or not len(b):
+            return a[:0]
+        size = domain_size(len(a) + len(b) - 1)
+        return trim(self.ifft(self.mul(self.fft(a, size), self.fft(b, size)), size))
+
+    def divide_by_vanishing_poly(self, p, n):
+        """DensePolynomial::divide_by_vanishing_poly for x^n - 1 -> (quotient, remainder)"""
+        if len(p) < n:
+            return p[:0], trim(p)
+        q = p[n:].copy()           # a copy: the accumulation below must not alias the tails it reads
+        for i in range(1, len(p) // n):
+            tail = p[n * (i + 1):]
+            if len(tail):
+                q[:len(tail)] = self.add(np.ascontiguousarray(q[:len(tail)]), np.ascontiguousarray(tail))
+        r = p[:n].copy()
+        k = min(n, len(q))
+        if k:
+            r[:k] = self.add(np.ascontiguousarray(r[:k]), np.ascontiguousarray(q[:k]))
+        return trim(q), trim(r)
+
+    def mul_by_vanishing_poly(self, p, n):
+        out = np.zeros((len(p) + n, 4), dtype=np.uint64)
+        out[n:] = p
+        if len(p):
+            out[:len(p)] = self.sub(np.ascontiguousarray(out[:len(p)]), np.ascontiguousarray(p))
+        return trim(out)
+
+    def add_const_terms(self, p, terms):
+        """p + sum c * x^k for a few (k, c) pairs with canonical int c (host-side scalar arithmetic)"""
+        n = max([len(p)] + [k + 1 for k, _ in terms])
+        out = pad(p, n)
+        for k, c in terms:
+            out[k] = self.f.mont(self.f.to_int(out[k]) + c)
+        return trim(out)
+
+    def batch_evals(self, size, x):
+        """arithmetic.rs:28-34: v_H(x) / (x - w^i)"""
+        den = self.inv(self.rsub(x, self.elements(size)))
+        return self.scale(den, self.f.vanishing_at(size, x))
+
+
+class Index:
+    """What the prover reads from `Index` (indexer.rs:29-69): the three square matrices and, per
+    matrix, the arithmetisation's evaluations on K and on B (arithmetic.rs:97-172)."""
+
+    def __init__(self, curve, num_constraints, num_variables, num_non_zeros, num_inputs, matrices, stars):
+        """matrices: {'a'|'b'|'c': CsrMatrix over the formatted variable numbering}
+        stars: {'a'|'b'|'c': {'row_evals_on_k', 'col_evals_on_k', 'val_evals_on_k', 'row_evals_on_b',
+                'col_evals_on_b', 'val_evals_on_b', 'row_col_evals_on_b'}} Montgomery arrays"""
+        self.curve = curve
+        self.num_constraints, self.num_variables, self.num_non_zeros = num_constraints, num_variables, num_non_zeros
+        self.x_size, self.h_size, self.k_size = domain_size(num_inputs), domain_size(num_variables), domain_size(num_non_zeros)
+        self.b_size = domain_size(3 * self.k_size - 3)
+        self.matrices, self.stars = matrices, stars
+        for s in (self.x_size, self.h_size, self.k_size, self.b_size):
+            if s.bit_length() - 1 > FR_TWO_ADICITY[curve]:
+                raise PolynomialDegreeTooLarge()
+        # transposed, H-reindexed matrices for the t accumulation of round 2 (prover.rs:259-269)
+        self.transposed = {}
+        for name, m in matrices.items():
+            rows = np.repeat(np.arange(m.n_rows, dtype=np.int64), np.diff(m.row_ptr.astype(np.int64)))
+            k = reindex_by_subdomain(self.h_size, self.x_size, m.col_idx.astype(np.int64))
+            order = np.argsort(k, kind="stable")
+            ptr = np.zeros(self.h_size + 1, dtype=np.uint32)
+            np.cumsum(np.bincount(k, minlength=self.h_size), out=ptr[1:])
+            self.transposed[name] = CsrMatrix(ptr, rows[order].astype(np.uint32), m.coeff[order])
+
+
+class ProverState:
+    pass
+
+
+def prover_init(ctx, index, formatted_input_mont, witness_mont):
+    """prover.rs:86-147 after synthesis and make_matrices_square: formatted_input = [one, inputs..],
+    witness = aux assignment (+ padding variables)."""
+    ni, nw = len(formatted_input_mont), len(witness_mont)
+    if index.num_constraints != index.matrices["a"].n_rows or index.num_constraints != ni + nw:
+        raise InstanceDoesNotMatchIndex()
+    st = ProverState()
+    st.ctx, st.index, st.ops = ctx, index, Ops(ctx, index.curve)
+    st.x, st.w = np.ascontiguousarray(formatted_input_mont), np.ascontiguousarray(witness_mont)
+    z = np.concatenate([st.x, st.w])
+    st.z_a = ctx.spmv(index.curve, index.matrices["a"], z)
+    st.z_b = ctx.spmv(index.curve, index.matrices["b"], z)
+    st.zk_bound = 1
+    return st
+
+
+def prover_first_round(st, rng):
+    """prover.rs:150-222.  rng.randrange(p) is called in the reference's order: the blinding constants of
+    w, z_a, z_b (DensePolynomial::rand(zk_bound - 1)), then the 3|H| + 2 zk_bound - 2 mask coefficients."""
+    o, idx = st.ops, st.index
+    p = o.f.p
+    H, X = idx.h_size, idx.x_size
+    x_poly = trim(o.ifft(st.x, X))
+    x_evals_on_h = o.fft(x_poly, H)
+    ratio = H // X
+    i = np.arange(H)
+    if H > X:
+        w_ext = pad(st.w, H - X)
+        src = np.where(i % ratio == 0, 0, i - i // ratio - 1)
+        gathered = np.ascontiguousarray(w_ext[src])
+    else:
+        gathered = np.zeros((H, 4), dtype=np.uint64)
+    w_minus_x = o.sub(gathered, x_evals_on_h)
+    w_minus_x[i % ratio == 0] = 0
+
+    def blind(poly):                                                 # + DensePolynomial::rand(zk_bound - 1) * v_H
+        c = rng.randrange(p)
+        return o.add_const_terms(poly, [(0, -c), (H, c)])
+
+    w_poly = blind(trim(o.ifft(w_minus_x, H)))
+    w_poly, rem = o.divide_by_vanishing_poly(w_poly, X)
+    assert not len(rem), "w is not divisible by v_X"                 # prover.rs:192
+    z_a_poly = blind(trim(o.ifft(st.z_a, H)))
+    z_b_poly = blind(trim(o.ifft(st.z_b, H)))
+    mask_degree = 3 * H + 2 * st.zk_bound - 3
+    mask_ints = [rng.randrange(p) for _ in range(mask_degree + 1)]
+    sigma = sum(mask_ints[k] for k in range(0, len(mask_ints), H)) % p     # remainder coefficient 0 mod (x^H - 1)
+    mask_ints[0] = (mask_ints[0] - sigma) % p
+    mask_poly = trim(st.ctx.fr_convert(idx.curve, ints_to_limbs(mask_ints), to_mont=True))
+    st.x_poly, st.w_poly, st.z_a_poly, st.z_b_poly, st.mask_poly = x_poly, w_poly, z_a_poly, z_b_poly, mask_poly
+    # (label, polynomial, degree_bound, hiding_bound) as in ProverFirstOracles
+    return [("w", w_poly, None, 1), ("z_a", z_a_poly, None, 1), ("z_b", z_b_poly, None, 1), ("mask", mask_poly, None, None)]
+
+
+def prover_second_round(st, alpha, eta_a, eta_b, eta_c):
+    """prover.rs:230-321; the verifier's first message as canonical ints"""
+    o, idx = st.ops, st.index
+    H, X = idx.h_size, idx.x_size
+    za, zb = st.z_a_poly, st.z_b_poly
+    m = o.scale(o.poly_mul(za, zb), eta_c)
+    k = min(len(m), len(za), len(zb))
+    if k:
+        low = o.axpy(o.axpy(np.ascontiguousarray(m[:k]), eta_a, np.ascontiguousarray(za[:k])), eta_b,
+                     np.ascontiguousarray(zb[:k]))
+        m = np.concatenate([low, m[k:]])
+    m_poly = trim(m)
+    r_alpha_evals = o.batch_evals(H, alpha)
+    r_alpha_poly = trim(o.ifft(r_alpha_evals, H))
+    t_evals = np.zeros((H, 4), dtype=np.uint64)
+    for name, eta in (("a", eta_a), ("b", eta_b), ("c", eta_c)):
+        t_evals = o.axpy(t_evals, eta, st.ctx.spmv(idx.curve, idx.transposed[name], r_alpha_evals))
+    t_poly = trim(o.ifft(t_evals, H))
+    z_poly = o.mul_by_vanishing_poly(st.w_poly, X)
+    k = min(len(z_poly), len(st.x_poly))
+    if k:
+        z_poly = np.concatenate([o.add(np.ascontiguousarray(z_poly[:k]), np.ascontiguousarray(st.x_poly[:k])), z_poly[k:]])
+    size = domain_size(max(len(st.mask_poly), len(r_alpha_poly) + len(m_poly), len(t_poly) + len(z_poly)))
+    ev = o.sub(o.mul(o.fft(r_alpha_poly, size), o.fft(m_poly, size)), o.mul(o.fft(t_poly, size), o.fft(z_poly, size)))
+    q1 = o.poly_add(st.mask_poly, trim(o.ifft(ev, size)))
+    h_1, x_g_1 = o.divide_by_vanishing_poly(q1, H)
+    g_1 = trim(x_g_1[1:])
+    st.t_poly, st.first_msg = t_poly, (alpha, eta_a, eta_b, eta_c)
+    return [("t", t_poly, None, None), ("g_1", g_1, H - 2, st.zk_bound), ("h_1", h_1, None, None)]
+
+
+def prover_third_round(st, beta):
+    """prover.rs:331-427"""
+    o, idx = st.ops, st.index
+    p = o.f.p
+    H, K, B = idx.h_size, idx.k_size, idx.b_size
+    alpha, eta_a, eta_b, eta_c = st.first_msg
+    vv = o.f.vanishing_at(H, alpha) * o.f.vanishing_at(H, beta) % p
+    stars = [idx.stars[n] for n in "abc"]
+    etas = [eta_a, eta_b, eta_c]
+    t_k = np.zeros((K, 4), dtype=np.uint64)
+    for s, eta in zip(stars, etas):
+        inv = o.inv(o.mul(o.rsub(beta, s["row_evals_on_k"]), o.rsub(alpha, s["col_evals_on_k"])))
+        t_k = o.axpy(t_k, eta, o.mul(s["val_evals_on_k"], inv))
+    t_poly = trim(o.ifft(o.scale(t_k, vv), K))
+    g_2 = trim(t_poly[1:])
+    # denom = beta * alpha - alpha * row - beta * col + row_col on B
+    den = []
+    for s in stars:
+        d = o.axpy(s["row_col_evals_on_b"], -alpha % p, s["row_evals_on_b"])
+        d = o.axpy(d, -beta % p, s["col_evals_on_b"])
+        den.append(o.addc(d, alpha * beta % p))
+    pairs = [(1, 2), (2, 0), (0, 1)]
+    a_evals = np.zeros((B, 4), dtype=np.uint64)
+    for s, eta, (u, v) in zip(stars, etas, pairs):
+        a_evals = o.axpy(a_evals, eta, o.mul(s["val_evals_on_b"], o.mul(den[u], den[v])))
+    a_poly = trim(o.ifft(o.scale(a_evals, vv), B))
+    b_poly = trim(o.ifft(o.mul(den[0], o.mul(den[1], den[2])), B))
+    h_2 = o.divide_by_vanishing_poly(o.poly_sub(a_poly, o.poly_mul(b_poly, t_poly)), K)[0]
+    return [("g_2", g_2, K - 2, None), ("h_2", h_2, None, None)]

@@ -171,6 +171,16 @@ int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* p
 /* ark_ff::batch_inversion (marlin/src/ahp/prover.rs:365-367): out[i] = 1 / in[i], zeros stay zero. */
 int zkb_fr_batch_inverse(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n);
 
+/* Elementwise Fr vector operations (the pointwise loops of marlin/src/ahp/prover.rs:246-305,357-411):
+ * op 0: a + b  1: a - b  2: a * b  3: s * a  4: a + s * b  5: s - a  6: a + s   (b / s may be NULL when unused) */
+int zkb_fr_vec_op(zkb_ctx* ctx, int curve, int op, const uint64_t* a_mont, const uint64_t* b_mont, const uint64_t* s_mont,
+                  uint64_t* out_mont, size_t n);
+/* out[i] = scale * base^i (scale may be NULL = 1): domain elements (EvaluationDomain::elements) and coset powers */
+int zkb_fr_powers(zkb_ctx* ctx, int curve, const uint64_t base_mont[4], const uint64_t* scale_mont, uint64_t* out_mont, size_t n);
+/* y = M x for a CSR matrix with Montgomery coefficients: the sparse accumulations of
+ * marlin/src/ahp/prover.rs:110-123 (z_A, z_B) and :259-269 (t, with the transposed matrices) */
+int zkb_spmv(zkb_ctx* ctx, int curve, const zkb_csr* m, const uint64_t* x_mont, size_t n_cols, uint64_t* y_mont);
+
 /* ---- diagnostics: single field / group operations of the device arithmetic on n operands, used by
  * the parity tests to check the GPU arithmetic against the CPU oracle in isolation.
  * field: 0 BN254 Fr, 1 BLS12-381 Fr, 2 BN254 Fq, 3 BLS12-381 Fq.

@@ -1,0 +1,62 @@
+"""CPU test of the Marlin host orchestration (ckb_zkp_b200/marlin.py) over a mock backend whose
+primitives are computed by the oracle: checks that the three AHP rounds call the device primitives
+with the right operands, independently of the CUDA kernels (those are checked in test_gpu_marlin.py)."""
+import random
+
+import pytest
+
+from ckb_zkp_b200 import marlin as zm
+from oracle.pyref import marlin as OM
+from oracle.pyref.fields import BLS12_381, BN254, FR
+from tests import helpers as H
+from tests.mock_backend import MockContext
+from tests.test_gpu_marlin import ReplayRng, device_index, mimc, mini, outside
+
+
+@pytest.mark.parametrize("cid,build", [(BLS12_381, mini), (BN254, lambda cs: mimc(cs, 12))])
+def test_rounds_over_mock_backend(cid, build):
+    p = FR[cid].p
+    rng = random.Random(31)
+    cs = OM.MarlinCS(p)
+    build(cs)
+    oidx = OM.index(cs, cid)
+    ost = OM.prover_init(oidx, cs)
+    idx = device_index(cid, oidx)
+    st = zm.prover_init(MockContext(), idx, H.fr_array(cid, cs.input), H.fr_array(cid, cs.witness))
+    Hs = idx.h_size
+    draws = [rng.randrange(p) for _ in range(3 + 3 * Hs)]
+    want = OM.prover_first_round(ost, draws[0], draws[1], draws[2], draws[3:])
+    got = zm.prover_first_round(st, ReplayRng(draws))
+    alpha, etas = outside(oidx["dh"], rng, p), [rng.randrange(p) for _ in range(3)]
+    want.update(OM.prover_second_round(ost, alpha, *etas))
+    got += zm.prover_second_round(st, alpha, *etas)
+    beta = outside(oidx["dh"], rng, p)
+    want.update(OM.prover_third_round(ost, beta))
+    got += zm.prover_third_round(st, beta)
+    polys = {label: H.fr_ints(cid, poly) for label, poly, _, _ in got}
+    for label in want:
+        assert polys[label] == want[label], label
+    assert OM.verifier_equality_check(oidx, cs.input[1:], polys, alpha, *etas, beta, rng.randrange(p))
+
+
+def test_marlin_oracle_rejects_a_bad_witness():
+    """the restated verifier_equality_check (ahp/verifier.rs:128-209) is a real test: it fails when the
+    witness does not satisfy the constraints or a prover polynomial is altered"""
+    cid = BLS12_381
+    p = FR[cid].p
+    rng = random.Random(2)
+    for bad in (False, True):
+        cs = OM.MarlinCS(p)
+        mini(cs)
+        if bad:
+            cs.witness[0] = 5                       # x = 5: 5 * (3 + 2) != 10
+        idx = OM.index(cs, cid)
+        st = OM.prover_init(idx, cs)
+        Hs = idx["dh"].size
+        polys = OM.prover_first_round(st, *[rng.randrange(p) for _ in range(3)], [rng.randrange(p) for _ in range(3 * Hs)])
+        alpha, etas = outside(idx["dh"], rng, p), [rng.randrange(p) for _ in range(3)]
+        polys.update(OM.prover_second_round(st, alpha, *etas))
+        beta = outside(idx["dh"], rng, p)
+        polys.update(OM.prover_third_round(st, beta))
+        ok = OM.verifier_equality_check(idx, cs.input[1:], polys, alpha, *etas, beta, rng.randrange(p))
+        assert ok == (not bad)
