@@ -312,7 +312,11 @@ def run_ours(args):
             ach = bytes_per / (ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "kernel": "k_accumulate (Pippenger bucket accumulation)", "achieved": ach,
                                 "peak": peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
-                                "unit": "GB/s", "frac": ach / peak, "traffic": None, "avg_launch_ms": ms,
+                                "unit": "GB/s", "frac": ach / peak,
+                                # dram__bytes_read + write of one G1 launch (a_query MSM, 2^20 pairs) from the ncu
+                                # --set full capture in profiles/r1_accumulate_v4_ncu_full.txt; by design far above
+                                # the algorithmic bytes: the window tables are gathered once per bucket entry
+                                "traffic": 2.694e9 if args.log_constraints == 20 else None, "avg_launch_ms": ms,
                                 "launches": prof_out["launches"], "share_of_step": prof_out["ms"] / dev_ms_max,
                                 "note": "MSM is integer-ALU bound: see DESIGN.md for the IMAD roofline"}
         else:
