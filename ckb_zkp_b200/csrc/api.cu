@@ -64,10 +64,19 @@ int zkb_init(int device, zkb_ctx** out) {
   zkb_ctx* ctx = new zkb_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  bool ok = cudaStreamCreateWithFlags(&ctx->main, cudaStreamNonBlocking) == cudaSuccess;
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  bool ok = cudaStreamCreateWithPriority(&ctx->main, cudaStreamNonBlocking, prio_greatest) == cudaSuccess;
   for (int i = 0; ok && i < kNumSideStreams; i++) {
-    ok = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+    ok = cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, prio_greatest) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  const char* no_bulk = getenv("ZKB_NO_BULK");
+  if (ok && prio_least != prio_greatest && !(no_bulk && atoi(no_bulk))) {
+    for (int i = 0; ok && i <= kNumSideStreams; i++)
+      ok = cudaStreamCreateWithPriority(&ctx->bulk[i], cudaStreamNonBlocking, prio_least) == cudaSuccess;
+    for (int i = 0; ok && i < kEventPool; i++)
+      ok = cudaEventCreateWithFlags(&ctx->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   ctx->pinned_bytes = 1 << 16;
@@ -101,6 +110,8 @@ void zkb_destroy(zkb_ctx* ctx) {
     if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (cudaEvent_t e : ctx->ev_pool) if (e) cudaEventDestroy(e);
+  for (cudaStream_t b : ctx->bulk) if (b) cudaStreamDestroy(b);
   if (ctx->main) cudaStreamDestroy(ctx->main);
   delete ctx;
 }

@@ -16,6 +16,7 @@
 namespace zkb {
 
 constexpr int kNumSideStreams = 6;
+constexpr int kEventPool = 256;       // rotating hand-off events between a caller's stream and the bulk stream
 constexpr int kSMs = 148;   // B200
 
 struct NttDomain;           // ntt.cu
@@ -29,6 +30,13 @@ struct zkb_ctx {
   cudaStream_t side[zkb::kNumSideStreams] = {};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[zkb::kNumSideStreams] = {};
+  // Low-priority twins of main (index 0) and of the side streams (index i + 1) for the machine-filling
+  // bucket-accumulation kernels: everything else (transforms, sorts, bucket reductions, proof assembly)
+  // sits on the high-priority streams, so those small grids take SM slots as accumulation blocks retire
+  // instead of queueing behind a whole accumulation kernel.
+  cudaStream_t bulk[zkb::kNumSideStreams + 1] = {};
+  cudaEvent_t ev_pool[zkb::kEventPool] = {};
+  unsigned ev_next = 0;
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
@@ -122,6 +130,24 @@ inline void prof_end(zkb_ctx* ctx, cudaStream_t st, double alg_bytes) {
   cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st);
   ctx->prof_used += 2;
   ctx->prof_alg_bytes += alg_bytes;
+}
+
+// Run what `enqueue` launches on the low-priority twin of `st`, ordered after the work already on `st` and before the
+// work that follows on `st`.  (A rotating event is safe to reuse: cudaStreamWaitEvent captures the record
+// that precedes it at call time.)
+template <class Fn>
+inline int on_bulk_stream(zkb_ctx* ctx, cudaStream_t st, Fn enqueue) {
+  cudaStream_t bulk = st == ctx->main ? ctx->bulk[0] : nullptr;
+  for (int i = 0; i < kNumSideStreams; i++)
+    if (st == ctx->side[i]) bulk = ctx->bulk[i + 1];
+  if (!bulk) return enqueue(st);
+  cudaEvent_t e0 = ctx->ev_pool[ctx->ev_next++ % kEventPool], e1 = ctx->ev_pool[ctx->ev_next++ % kEventPool];
+  ZKB_CUDA(ctx, cudaEventRecord(e0, st));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(bulk, e0, 0));
+  ZKB_TRY(enqueue(bulk));
+  ZKB_CUDA(ctx, cudaEventRecord(e1, bulk));
+  ZKB_CUDA(ctx, cudaStreamWaitEvent(st, e1, 0));
+  return ZKB_OK;
 }
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

@@ -176,8 +176,8 @@ struct alignas(16) Fp {
     return mul(a, o);
   }
 
-  // a^e, e given as N 32-bit limbs through a constexpr accessor (Fermat inversion)
-  ZKB_HD static Fp inv(const Fp& a) {
+  // a^(p-2) (Fermat); kept as the independent cross-check of inv()
+  ZKB_HD static Fp inv_fermat(const Fp& a) {
     Fp r = one();
     for (int i = N - 1; i >= 0; i--) {
       uint32_t e = P::pm2(i);
@@ -187,6 +187,70 @@ struct alignas(16) Fp {
       }
     }
     return r;
+  }
+  // a^-1 (Montgomery in, Montgomery out; 0 -> 0) by a branch-free binary extended Euclid.
+  // Invariants: x1 * a == u and x2 * a == v (mod p), v odd.  One round: if u is odd subtract the
+  // smaller of (u, v) from the larger into u (which makes it even; v takes the old u when u < v),
+  // same on (x1, x2) mod p, then halve u and x1.  len(u) + len(v) drops every round, so at most
+  // 2 * BITS rounds run until u == 0, v == gcd == 1, x2 == a^-1.  Only add / logic / shift
+  // instructions: on the GPU this is ~10x shorter than the 1.5 * BITS dependent multiplications of
+  // the Fermat ladder and leaves the multiplier pipe to other warps.
+  ZKB_HD static Fp inv(const Fp& a) {
+    uint32_t u[N], v[N], x1[N], x2[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { u[i] = a.v[i]; v[i] = P::mod(i); x1[i] = i == 0 ? 1u : 0u; x2[i] = 0; }
+    for (int round = 0; round < 2 * P::BITS + 2; round++) {
+      uint32_t nz = 0;
+#pragma unroll
+      for (int i = 0; i < N; i++) nz |= u[i];
+      if (nz == 0) break;
+      const uint32_t odd = 0u - (u[0] & 1u);
+      // borrow of u - v
+      ptx::sub_cc(u[0], v[0]);
+#pragma unroll
+      for (int i = 1; i < N; i++) ptx::subc_cc(u[i], v[i]);
+      const uint32_t sw = odd & ptx::subc(0, 0);        // all ones when u is odd and u < v
+      // (u, v) <- (A - (B & odd), B) with (A, B) = sw ? (v, u) : (u, v)
+      uint32_t A[N], B[N];
+#pragma unroll
+      for (int i = 0; i < N; i++) { A[i] = (v[i] & sw) | (u[i] & ~sw); B[i] = (u[i] & sw) | (v[i] & ~sw); }
+      u[0] = ptx::sub_cc(A[0], B[0] & odd);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) u[i] = ptx::subc_cc(A[i], B[i] & odd);
+      u[N - 1] = ptx::subc(A[N - 1], B[N - 1] & odd);
+#pragma unroll
+      for (int i = 0; i < N; i++) v[i] = B[i];
+      // the same on (x1, x2), modulo p
+#pragma unroll
+      for (int i = 0; i < N; i++) { A[i] = (x2[i] & sw) | (x1[i] & ~sw); B[i] = (x1[i] & sw) | (x2[i] & ~sw); }
+      x1[0] = ptx::sub_cc(A[0], B[0] & odd);
+#pragma unroll
+      for (int i = 1; i < N; i++) x1[i] = ptx::subc_cc(A[i], B[i] & odd);
+      const uint32_t borrow = ptx::subc(0, 0);
+      x1[0] = ptx::add_cc(x1[0], P::mod(0) & borrow);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) x1[i] = ptx::addc_cc(x1[i], P::mod(i) & borrow);
+      x1[N - 1] = ptx::addc(x1[N - 1], P::mod(N - 1) & borrow);
+#pragma unroll
+      for (int i = 0; i < N; i++) x2[i] = B[i];
+      // halve u (even now) and x1 (add p first when odd; x1 + p < 2^(32N))
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) u[i] = (u[i] >> 1) | (u[i + 1] << 31);
+      u[N - 1] >>= 1;
+      const uint32_t xo = 0u - (x1[0] & 1u);
+      x1[0] = ptx::add_cc(x1[0], P::mod(0) & xo);
+#pragma unroll
+      for (int i = 1; i < N - 1; i++) x1[i] = ptx::addc_cc(x1[i], P::mod(i) & xo);
+      x1[N - 1] = ptx::addc(x1[N - 1], P::mod(N - 1) & xo);
+#pragma unroll
+      for (int i = 0; i < N - 1; i++) x1[i] = (x1[i] >> 1) | (x1[i + 1] << 31);
+      x1[N - 1] >>= 1;
+    }
+    // x2 = (aR)^-1 = a^-1 R^-1; two Montgomery products with R^2 bring it to a^-1 R
+    Fp r;
+#pragma unroll
+    for (int i = 0; i < N; i++) r.v[i] = x2[i];
+    return mul(mul(r, r2()), r2());
   }
   // a^e for a runtime 64-bit exponent
   ZKB_HD static Fp pow_u64(const Fp& a, uint64_t e) {

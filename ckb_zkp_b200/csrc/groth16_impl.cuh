@@ -137,24 +137,27 @@ __global__ void k_g16_coeffs(const Fp<FrP>* scal, const Affine<Fq>* a0, const Af
 }
 
 // g_c = s*g_a + r*g1_b - r*s*delta + l_acc + h_acc; into_affine of (g_a, g2_b, g_c)  (prover.rs:195-210)
+// `first` selects the blocks: proof_a / proof_b (blocks 0, 1) only need the coefficients and are converted
+// off the critical path; proof_c (block 2) waits for every MSM.
 template <class Fq, class Fq2>
-__global__ void k_g16_finish(G16Results<Fq, Fq2>* res) {
+__global__ void k_g16_finish(G16Results<Fq, Fq2>* res, unsigned first) {
   if (threadIdx.x) return;
-  if (blockIdx.x == 0) {
+  const unsigned blk = blockIdx.x + first;
+  if (blk == 0) {
     XYZZ<Fq> g = ld_vec_rw(&res->g_a);
     Affine<Fq> a;
     pt_to_affine(a, g);
     st_vec(&res->proof_a, a);
     res->inf[0] = g.is_inf();
   }
-  if (blockIdx.x == 1) {
+  if (blk == 1) {
     XYZZ<Fq2> g = ld_vec_rw(&res->g2_b);
     Affine<Fq2> a;
     pt_to_affine(a, g);
     st_vec(&res->proof_b, a);
     res->inf[1] = g.is_inf();
   }
-  if (blockIdx.x == 2) {
+  if (blk == 2) {
     XYZZ<Fq> g = ld_vec_rw(&res->s_g_a);
     XYZZ<Fq> t = ld_vec_rw(&res->r_g1_b);
     pt_add(g, t);
@@ -319,14 +322,24 @@ struct Groth16Impl {
     const uint32_t* zr = (const uint32_t*)s->z_repr.p;
     auto clamp = [](size_t n, const zkb_srs* srs, size_t off) { size_t a = srs->n > off ? srs->n - off : 0; return n < a ? n : a; };
     // The four MSMs over the assignment are independent of each other and of witness_map: one
-    // side stream each, so the low-parallelism tails of one (bucket reduction, final sums) overlap
-    // the bucket accumulation of another; witness_map and the H MSM stay on the main stream.
+    // high-priority side stream each for their sorts and bucket reductions, while the accumulation
+    // kernels of all five MSMs queue on the low-priority bulk stream in the order of the calls below
+    // (b_g2, a, b_g1, h, l).  a, b_g1 and b_g2 go first because calculate_coeff's scalar multiplications
+    // (s * g_a, r * g1_b) hang off them: they run on side[5] under the H and L accumulations, so that
+    // after the last bucket reduction only the five additions and the inversion of proof.c remain.
     ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    for (int i = 1; i <= 4; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+    for (int i = 1; i <= 5; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
     ZKB_TRY(g2->msm_run(ctx, ctx->side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
     ZKB_TRY(g1->msm_run(ctx, ctx->side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
-    ZKB_TRY(g1->msm_run(ctx, ctx->side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
     ZKB_TRY(g1->msm_run(ctx, ctx->side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
+    for (int i : {0, 1, 2, 4}) {
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+      ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[5], ctx->ev_join[i], 0));
+    }
+    ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, ctx->side[5], (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
+               (const Affine<Fq>*)pk->b_g1->table, (const Affine<Fq2>*)pk->b_g2->table,
+               (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles, res);
+    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 2, 32, 0, ctx->side[5], res, 0u);
     if (s->pending[0]) {
       ZKB_TRY(upload_csr(ctx, st, &s->A, s->pending[0]));
       ZKB_TRY(upload_csr(ctx, st, &s->B, s->pending[1]));
@@ -335,11 +348,12 @@ struct Groth16Impl {
     }
     ZKB_TRY(compute_h(ctx, st));
     ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
-    ZKB_TRY(join_streams(ctx, 5));
-    ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, st, (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
-               (const Affine<Fq>*)pk->b_g1->table, (const Affine<Fq2>*)pk->b_g2->table,
-               (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles, res);
-    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 3, 32, 0, st, res);
+    ZKB_TRY(g1->msm_run(ctx, ctx->side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    for (int i : {3, 5}) {
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+      ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+    }
+    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 1, 32, 0, st, res, 2u);
     return ZKB_OK;
   }
 

@@ -159,10 +159,14 @@ static __global__ void k_scan_finish(uint32_t* offsets, uint32_t n, const uint32
   if (i < n) {
     uint32_t v = offsets[i] + tile_sums[i / kScanTile];
     offsets[i] = v;
-    cursor[i] = v;
+    if (cursor) cursor[i] = v;
   }
   if (i == 0) offsets[n] = tile_sums[n_tiles];
 }
+
+}  // namespace zkb
+#include "msm_affine.cuh"
+namespace zkb {
 
 // ------------------------------------------------------------------------------------------
 // bucket scheduling: order the regular buckets by decreasing size, list the big ones
@@ -248,8 +252,9 @@ static __global__ void k_big_chunk_map(const uint32_t* __restrict__ offsets, con
 // ------------------------------------------------------------------------------------------
 // bucket accumulation
 // ------------------------------------------------------------------------------------------
-// one thread per regular bucket, in order of decreasing size
-template <class F, int MIN_BLOCKS>
+// one thread per regular bucket, in order of decreasing size.  DIRECT: the lists are the dense output of
+// the pair levels (entry = position, no sign, identities possible) instead of (negate | table index) entries.
+template <class F, int MIN_BLOCKS, bool DIRECT = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS)
 k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
              const uint32_t* __restrict__ order, const MsmSched* __restrict__ sched,
@@ -259,7 +264,7 @@ k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ 
   uint32_t b = order[t];
   uint32_t pos = offsets[b], end = offsets[b + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
-  uint32_t e = entries[pos];
+  uint32_t e = DIRECT ? pos : entries[pos];
   Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
   for (;;) {
     pos++;
@@ -267,10 +272,10 @@ k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ 
     Affine<F> p_next;
     bool more = pos < end;
     if (more) {                                   // fetch the next base while this one is added
-      e_next = entries[pos];
+      e_next = DIRECT ? pos : entries[pos];
       p_next = ld_vec(&table[e_next & 0x7fffffffu]);
     }
-    acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+    if (!DIRECT || !p.is_inf()) acc.madd_xy(p.x, p.y, (e >> 31) != 0);
     if (!more) break;
     e = e_next;
     p = p_next;
@@ -295,7 +300,7 @@ __device__ __forceinline__ void block_sum(XYZZ<F>& acc, XYZZ<F>* sh) {
 }
 
 // one block per 2048-entry chunk of a big bucket -> partial[chunk]
-template <class F>
+template <class F, bool DIRECT = false>
 __global__ void __launch_bounds__(kChunkThreads)
 k_big_chunks(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets, const MsmSched* __restrict__ sched,
              const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_chunk_off,
@@ -308,9 +313,9 @@ k_big_chunks(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ 
     uint32_t lo = offsets[b] + k * kChunk, hi = min(lo + (uint32_t)kChunk, offsets[b + 1]);
     XYZZ<F> acc = XYZZ<F>::inf();
     for (uint32_t pos = lo + threadIdx.x; pos < hi; pos += kChunkThreads) {    // coalesced entry reads
-      uint32_t e = entries[pos];
+      uint32_t e = DIRECT ? pos : entries[pos];
       Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
-      acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+      if (!DIRECT || !p.is_inf()) acc.madd_xy(p.x, p.y, (e >> 31) != 0);
     }
     block_sum<F, kChunkThreads>(acc, sh);
     if (threadIdx.x == 0) st_vec(&partial[ch], acc);
@@ -473,6 +478,27 @@ inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
   return best_c;
 }
 
+// Pair levels before the XYZZ accumulation: each level moves half of the remaining additions to the
+// cheaper batched-affine form but costs a scan and a kernel of its own, so stop when the lists are short
+// (average load: entries per bucket).  ZKB_MSM_PAIR_LEVELS overrides (0 = XYZZ only).
+inline int msm_pair_levels(size_t max_entries, uint32_t n_buckets) {
+  if (max_entries >= (size_t(1) << 31)) return 0;       // meta packs the source position into 31 bits
+  const char* e = getenv("ZKB_MSM_PAIR_LEVELS");        // read per call: the tests sweep it
+  const int forced = e ? atoi(e) : -1;
+  if (forced >= 0) return forced > 12 ? 12 : forced;
+  // Default: none.  Measured on B200 (2^20 BLS12-381 G1): the level kernels reach ~55 % of the
+  // multiplier pipe against 83 % for the XYZZ loop (one dependent multiplication chain per thread instead of
+  // three), which cancels the 40 % saving in multiplications: 5.1 ms with three levels vs 4.9 ms without.
+  (void)n_buckets;
+  return 0;
+}
+
+inline int pair_level_occupancy(const void* kernel) {
+  int blocks = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kPairThreads, 0) != cudaSuccess || blocks < 1) blocks = 1;
+  return blocks;
+}
+
 template <class F, class FrP>
 struct MsmEngine {
   using Fr = Fp<FrP>;
@@ -538,12 +564,72 @@ struct MsmEngine {
     ZKB_LAUNCH(ctx, (k_digits<true, Fr>), dig_blocks, 256, 0, st, d_scalars, (uint32_t)n, srs->inf, g,
                (uint32_t)base_offset, scalars_mont, cursor, entries);
 
+    // ---- batched-affine pair levels (msm_affine.cuh): each halves the bucket lists
+    const uint32_t* acc_off = offsets;          // lists that the XYZZ accumulation below consumes
+    const Aff* acc_pts = (const Aff*)srs->table;
+    size_t acc_max = max_entries;               // upper bound of their total length
+    const int levels = msm_pair_levels(max_entries, n_buckets);
+    if (levels > 0) {
+      auto halved = [&](size_t e) { return (e + (e < n_buckets ? e : (size_t)n_buckets) + 1) / 2; };
+      const size_t e1 = halved(max_entries), e2 = halved(e1);
+      uint32_t *off_a, *off_b, *meta;
+      F* prefix;
+      Aff *pts_a, *pts_b;
+      ZKB_TRY(ws.alloc(&off_a, (size_t)n_buckets + 1));
+      ZKB_TRY(ws.alloc(&off_b, (size_t)n_buckets + 1));
+      ZKB_TRY(ws.alloc(&meta, e1));
+      ZKB_TRY(ws.alloc(&prefix, e1));
+      ZKB_TRY(ws.alloc(&pts_a, e1));
+      ZKB_TRY(ws.alloc(&pts_b, levels > 1 ? e2 : 1));
+      const uint32_t* off_in = offsets;
+      size_t e_out = e1;
+      for (int lvl = 0; lvl < levels; lvl++) {
+        uint32_t* off_out = (lvl & 1) ? off_b : off_a;
+        Aff* pts_out = (lvl & 1) ? pts_b : pts_a;
+        ZKB_LAUNCH(ctx, k_pair_sizes, ceil_div(n_buckets, 256), 256, 0, st, off_in, n_buckets, off_out);
+        ZKB_LAUNCH(ctx, k_scan_tiles, n_tiles, kScanThreads, 0, st, off_out, n_buckets, tile_sums);
+        ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, tile_sums, n_tiles);
+        ZKB_LAUNCH(ctx, k_scan_finish, ceil_div(n_buckets, 256), 256, 0, st, off_out, n_buckets, tile_sums, n_tiles,
+                   (uint32_t*)nullptr);
+        // one resident wave; the kernel derives the slots per thread from the list length on the device
+        {
+          static bool pf_set = false;
+          if (!pf_set) {
+            pf_set = true;
+            if (const char* e = getenv("ZKB_PAIR_PF")) { int v = atoi(e); cudaMemcpyToSymbol(g_pair_prefetch, &v, sizeof v); }
+          }
+        }
+        ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
+          prof_begin(ctx, bs);
+          if (lvl == 0) {
+            static const int occ = pair_level_occupancy((const void*)k_pair_level<F, true>);
+            ZKB_LAUNCH(ctx, (k_pair_level<F, true>), (unsigned)(ctx->sm_count * occ), kPairThreads, 0, bs,
+                       (PairSrc<F, true>{entries, (const Aff*)srs->table}), off_in, (const uint32_t*)off_out, n_buckets, meta,
+                       prefix, pts_out);
+          } else {
+            static const int occ = pair_level_occupancy((const void*)k_pair_level<F, false>);
+            ZKB_LAUNCH(ctx, (k_pair_level<F, false>), (unsigned)(ctx->sm_count * occ), kPairThreads, 0, bs,
+                       (PairSrc<F, false>{nullptr, acc_pts}), off_in, (const uint32_t*)off_out, n_buckets, meta, prefix,
+                       pts_out);
+          }
+          prof_end(ctx, bs, 0.0);
+          return ZKB_OK;
+        }));
+        off_in = off_out;
+        acc_off = off_out;
+        acc_pts = pts_out;
+        acc_max = e_out;
+        e_out = halved(e_out);
+      }
+    }
+    const bool direct = levels > 0;
+
     // schedule: regular buckets by decreasing size, big buckets in chunks
     uint32_t *size_hist, *order, *big_list, *big_chunk_off, *chunk_slot;
     MsmSched* sched;
-    const uint32_t big = msm_big_threshold(max_entries);
-    const uint32_t max_big = (uint32_t)(max_entries / (big + 1)) + 1;
-    const uint32_t max_chunks = (uint32_t)(max_entries / kChunk) + max_big;
+    const uint32_t big = msm_big_threshold(acc_max);
+    const uint32_t max_big = (uint32_t)(acc_max / (big + 1)) + 1;
+    const uint32_t max_chunks = (uint32_t)(acc_max / kChunk) + max_big;
     ZKB_TRY(ws.alloc(&size_hist, (size_t)kSizeBins + 4));       // bins followed by the MsmSched block
     sched = reinterpret_cast<MsmSched*>(size_hist + kSizeBins);
     ZKB_TRY(ws.alloc(&order, n_buckets));
@@ -554,44 +640,53 @@ struct MsmEngine {
     {
       unsigned hist_blocks = ceil_div(n_buckets, 1024);
       if (hist_blocks > (unsigned)ctx->sm_count * 2) hist_blocks = ctx->sm_count * 2;
-      ZKB_LAUNCH(ctx, k_size_hist, hist_blocks, 1024, 0, st, offsets, n_buckets, big, size_hist, sched, big_list,
+      ZKB_LAUNCH(ctx, k_size_hist, hist_blocks, 1024, 0, st, acc_off, n_buckets, big, size_hist, sched, big_list,
                  big_chunk_off);
     }
     ZKB_LAUNCH(ctx, k_size_scan, 1, 1024, 0, st, size_hist, big, sched);
-    ZKB_LAUNCH(ctx, k_size_scatter, ceil_div(n_buckets, 256), 256, 0, st, offsets, n_buckets, big, size_hist, order);
-    ZKB_LAUNCH(ctx, k_big_chunk_map, ceil_div(max_big, 256), 256, 0, st, offsets, sched, big_list, big_chunk_off, chunk_slot);
+    ZKB_LAUNCH(ctx, k_size_scatter, ceil_div(n_buckets, 256), 256, 0, st, acc_off, n_buckets, big, size_hist, order);
+    ZKB_LAUNCH(ctx, k_big_chunk_map, ceil_div(max_big, 256), 256, 0, st, acc_off, sched, big_list, big_chunk_off, chunk_slot);
 
     // accumulate
     Pt *bucket_acc, *partial;
     ZKB_TRY(ws.alloc(&bucket_acc, n_buckets));
     ZKB_TRY(ws.alloc(&partial, max_chunks));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
-    prof_begin(ctx, st);
-    {
+    // the accumulation kernel fills the machine: it goes to the low-priority bulk stream (common.cuh)
+    ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
       using FC = typename CallVariant<F>::type;
       static_assert(sizeof(Affine<FC>) == sizeof(Aff) && sizeof(XYZZ<FC>) == sizeof(Pt), "call variant layout");
       // tuning switches (defaults chosen from measurements): multiplication as a call,
       // and a register cap that trades a few spills for a fourth resident block per SM
       static const int use_call = []() { const char* e = getenv("ZKB_ACC_CALL"); return e ? atoi(e) : 0; }();
       static const int occ4 = []() { const char* e = getenv("ZKB_ACC_OCC4"); return e ? atoi(e) : 0; }();
-      if (use_call)
-        ZKB_LAUNCH(ctx, (k_accumulate<FC, 3>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+      prof_begin(ctx, bs);
+      if (direct)
+        ZKB_LAUNCH(ctx, (k_accumulate<F, 1, true>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)nullptr, acc_off,
+                   order, sched, acc_pts, bucket_acc);
+      else if (use_call)
+        ZKB_LAUNCH(ctx, (k_accumulate<FC, 3>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets, order, sched,
                    (const Affine<FC>*)srs->table, (XYZZ<FC>*)bucket_acc);
       else if (occ4)
-        ZKB_LAUNCH(ctx, (k_accumulate<F, 4>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+        ZKB_LAUNCH(ctx, (k_accumulate<F, 4>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets, order, sched,
                    (const Aff*)srs->table, bucket_acc);
       else
-        ZKB_LAUNCH(ctx, (k_accumulate<F, 1>), ceil_div(n_buckets, 128), 128, 0, st, entries, offsets, order, sched,
+        ZKB_LAUNCH(ctx, (k_accumulate<F, 1>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets, order, sched,
                    (const Aff*)srs->table, bucket_acc);
-    }
-    prof_end(ctx, st, (double)n * (32.0 + sizeof(Aff)));   // one read of each (scalar, base) pair
+      prof_end(ctx, bs, (double)n * (32.0 + sizeof(Aff)));   // one read of each (scalar, base) pair
+      return ZKB_OK;
+    }));
     {
       // grids are upper bounds read against device-side counts (no host round trip)
       unsigned chunk_blocks = max_chunks < (unsigned)ctx->sm_count * 8 ? max_chunks : ctx->sm_count * 8;
       unsigned fold_blocks = max_big < (unsigned)ctx->sm_count * 4 ? max_big : ctx->sm_count * 4;
-      ZKB_LAUNCH(ctx, (k_big_chunks<F>), chunk_blocks, kChunkThreads, 0, st, entries, offsets, sched, big_list,
-                 big_chunk_off, chunk_slot, (const Aff*)srs->table, partial);
-      ZKB_LAUNCH(ctx, (k_big_fold<F>), fold_blocks, kChunkThreads, 0, st, offsets, sched, big_list, big_chunk_off,
+      if (direct)
+        ZKB_LAUNCH(ctx, (k_big_chunks<F, true>), chunk_blocks, kChunkThreads, 0, st, (const uint32_t*)nullptr, acc_off, sched,
+                   big_list, big_chunk_off, chunk_slot, acc_pts, partial);
+      else
+        ZKB_LAUNCH(ctx, (k_big_chunks<F>), chunk_blocks, kChunkThreads, 0, st, entries, offsets, sched, big_list,
+                   big_chunk_off, chunk_slot, (const Aff*)srs->table, partial);
+      ZKB_LAUNCH(ctx, (k_big_fold<F>), fold_blocks, kChunkThreads, 0, st, acc_off, sched, big_list, big_chunk_off,
                  (const Pt*)partial, bucket_acc);
     }
 

@@ -207,6 +207,107 @@ class Index:
             self.transposed[name] = CsrMatrix(ptr, rows[order].astype(np.uint32), m.coeff[order])
 
 
+def make_matrices_square(mats, num_variables):
+    """constraint_systems.rs:9-31 on CSR matrices: pad with empty constraints (or report how many padding
+    variables the caller must append to the witness) so that #constraints == #variables."""
+    nc = mats[0].n_rows
+    extra_vars = max(nc - num_variables, 0)
+    if num_variables > nc:
+        pad_rows = num_variables - nc
+        mats = [CsrMatrix(np.concatenate([m.row_ptr, np.full(pad_rows, m.row_ptr[-1], dtype=np.uint32)]), m.col_idx, m.coeff)
+                for m in mats]
+    return mats, extra_vars
+
+
+def balance_matrices(a, b):
+    """constraint_systems.rs:100-114: while A is the denser matrix, swap row i of A and B.  `denser` is only
+    re-evaluated after a swap, so nothing happens unless A starts out denser (the reference's behaviour)."""
+    da, db = a.nnz, b.nnz
+    if not da > db:
+        return a, b
+    la, lb = np.diff(a.row_ptr.astype(np.int64)), np.diff(b.row_ptr.astype(np.int64))
+    swap = np.zeros(len(la), dtype=bool)
+    denser = True
+    for i in range(len(la)):
+        if not denser:
+            break
+        swap[i] = True
+        da += lb[i] - la[i]
+        db += la[i] - lb[i]
+        denser = da > db
+
+    def merge(first, second, take_second):
+        lens = np.where(take_second, np.diff(second.row_ptr.astype(np.int64)), np.diff(first.row_ptr.astype(np.int64)))
+        ptr = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        cols = np.zeros(ptr[-1], dtype=np.uint32)
+        coeff = np.zeros((ptr[-1], 4), dtype=np.uint64)
+        for src, mask in ((first, ~take_second), (second, take_second)):
+            sp = src.row_ptr.astype(np.int64)
+            rows = np.flatnonzero(mask)
+            cnt = (sp[rows + 1] - sp[rows])
+            src_pos = np.repeat(sp[rows], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+            dst_pos = np.repeat(ptr[rows], cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+            cols[dst_pos] = src.col_idx[src_pos]
+            coeff[dst_pos] = src.coeff[src_pos]
+        return CsrMatrix(ptr.astype(np.uint32), cols, coeff)
+
+    return merge(a, b, swap), merge(b, a, swap)
+
+
+def sort_rows_by_column(m):
+    """process_matrices' per-row stable sort by variable index (constraint_systems.rs:92-96)"""
+    rows = np.repeat(np.arange(m.n_rows, dtype=np.int64), np.diff(m.row_ptr.astype(np.int64)))
+    order = np.lexsort((np.arange(len(rows)), m.col_idx.astype(np.int64), rows))
+    return CsrMatrix(m.row_ptr, m.col_idx[order], m.coeff[order])
+
+
+def compose_matrix_polynomials(ops, m, x_size, h_size, k_size, b_size, h_elems, inv_diag):
+    """arithmetic.rs:97-172 with every field operation on the GPU: row / col / val / row_col evaluations on K,
+    interpolated over K and evaluated over B.  h_elems = w_H^i, inv_diag[j] = 1 / u_H(w^j, w^j)."""
+    nnz = m.nnz
+    rows = np.repeat(np.arange(m.n_rows, dtype=np.int64), np.diff(m.row_ptr.astype(np.int64)))
+    j = reindex_by_subdomain(h_size, x_size, m.col_idx.astype(np.int64))
+    row_vec = np.empty((k_size, 4), dtype=np.uint64)
+    col_vec = np.empty((k_size, 4), dtype=np.uint64)
+    val_vec = np.zeros((k_size, 4), dtype=np.uint64)
+    row_vec[:nnz] = h_elems[j]                   # note the reference's naming: "row" holds the column's element
+    col_vec[:nnz] = h_elems[rows]
+    row_vec[nnz:] = h_elems[0]
+    col_vec[nnz:] = h_elems[0]
+    if nnz:
+        val_vec[:nnz] = ops.mul(np.ascontiguousarray(m.coeff), np.ascontiguousarray(inv_diag[j]))
+    row_col_vec = ops.mul(row_vec, col_vec)
+    out = {"row_evals_on_k": row_vec, "col_evals_on_k": col_vec, "val_evals_on_k": val_vec}
+    for name, vec in (("row", row_vec), ("col", col_vec), ("val", val_vec), ("row_col", row_col_vec)):
+        poly = trim(ops.ifft(vec, k_size))
+        out[name] = poly
+        out[name + "_evals_on_b"] = ops.fft(poly, b_size)
+    return out
+
+
+def index(ctx, curve, a, b, c, num_inputs, num_variables):
+    """AHP::index (indexer.rs:71-116) for already synthesised matrices (CsrMatrix over the formatted variable
+    numbering: inputs first, then witness).  Returns (Index, number of padding witness variables)."""
+    (a, b, c), extra_vars = make_matrices_square([a, b, c], num_variables)
+    num_variables += extra_vars
+    a, b = balance_matrices(a, b)
+    a, b, c = sort_rows_by_column(a), sort_rows_by_column(b), sort_rows_by_column(c)
+    nnz = max(a.nnz, b.nnz, c.nnz)
+    ops = Ops(ctx, curve)
+    x_size, h_size, k_size = domain_size(num_inputs), domain_size(num_variables), domain_size(nnz)
+    b_size = domain_size(3 * k_size - 3)
+    for s_ in (x_size, h_size, k_size, b_size):
+        if s_.bit_length() - 1 > FR_TWO_ADICITY[curve]:
+            raise PolynomialDegreeTooLarge()
+    h_elems = ops.elements(h_size)
+    # u_H(w^j, w^j) = |H| * w^(-j) (arithmetic.rs:19-26 on the diagonal; :105-111 builds it reversed)
+    inv_diag = ops.scale(h_elems, pow(h_size, -1, ops.f.p))
+    stars = {name: compose_matrix_polynomials(ops, m, x_size, h_size, k_size, b_size, h_elems, inv_diag)
+             for name, m in (("a", a), ("b", b), ("c", c))}
+    return Index(curve, a.n_rows, num_variables, nnz, num_inputs, {"a": a, "b": b, "c": c}, stars), extra_vars
+
+
 class ProverState:
     pass
 
@@ -256,10 +357,19 @@ def prover_first_round(st, rng):
     z_a_poly = blind(trim(o.ifft(st.z_a, H)))
     z_b_poly = blind(trim(o.ifft(st.z_b, H)))
     mask_degree = 3 * H + 2 * st.zk_bound - 3
-    mask_ints = [rng.randrange(p) for _ in range(mask_degree + 1)]
-    sigma = sum(mask_ints[k] for k in range(0, len(mask_ints), H)) % p     # remainder coefficient 0 mod (x^H - 1)
-    mask_ints[0] = (mask_ints[0] - sigma) % p
-    mask_poly = trim(st.ctx.fr_convert(idx.curve, ints_to_limbs(mask_ints), to_mont=True))
+    if hasattr(rng, "field_array"):
+        # bulk draw for large instances: rng.field_array(n) -> canonical uint64[n, 4] residues (the host RNG of
+        # DensePolynomial::rand, prover.rs:202, without a Python-level loop)
+        mask_canon = np.ascontiguousarray(rng.field_array(mask_degree + 1))
+        heads = np.ascontiguousarray(mask_canon[0::H])
+        sigma = sum(int.from_bytes(h.tobytes(), "little") for h in heads) % p
+        mask_canon[0] = ints_to_limbs([(int.from_bytes(mask_canon[0].tobytes(), "little") - sigma) % p])[0]
+        mask_poly = trim(st.ctx.fr_convert(idx.curve, mask_canon, to_mont=True))
+    else:
+        mask_ints = [rng.randrange(p) for _ in range(mask_degree + 1)]
+        sigma = sum(mask_ints[k] for k in range(0, len(mask_ints), H)) % p     # remainder coefficient 0 mod (x^H - 1)
+        mask_ints[0] = (mask_ints[0] - sigma) % p
+        mask_poly = trim(st.ctx.fr_convert(idx.curve, ints_to_limbs(mask_ints), to_mont=True))
     st.x_poly, st.w_poly, st.z_a_poly, st.z_b_poly, st.mask_poly = x_poly, w_poly, z_a_poly, z_b_poly, mask_poly
     # (label, polynomial, degree_bound, hiding_bound) as in ProverFirstOracles
     return [("w", w_poly, None, 1), ("z_a", z_a_poly, None, 1), ("z_b", z_b_poly, None, 1), ("mask", mask_poly, None, None)]

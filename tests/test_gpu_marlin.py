@@ -203,3 +203,37 @@ def test_marlin_commit_and_open_flow(ctx):
         assert ow == OK.exponent_point(ock, w_exp)
         assert OK.kzg_check_in_exponent(ock, acc_c % p, point, acc_v % p, w_exp, orv)
     ck.free()
+
+
+@pytest.mark.parametrize("cid,build", [(BLS12_381, mini), (BN254, lambda cs: mimc(cs, 60))])
+def test_gpu_indexer_matches_oracle(ctx, cid, build):
+    """AHP::index (indexer.rs:71-116, arithmetic.rs:97-172) computed with the GPU primitives from CSR matrices
+    == the oracle's index: squared matrices, domain sizes and all 7 x 3 evaluation tables."""
+    fr = FR[cid]
+    cs = OM.MarlinCS(fr.p)
+    build(cs)
+    ni, nv, nc = len(cs.input), len(cs.input) + len(cs.witness), len(cs.a)
+
+    def csr(rows):
+        ptr, cols, vals = [0], [], []
+        for row in rows:
+            for co, v in row:
+                cols.append(v[1] if v[0] == "in" else ni + v[1])
+                vals.append(co)
+            ptr.append(len(cols))
+        return CsrMatrix(np.asarray(ptr, dtype=np.uint32), np.asarray(cols, dtype=np.uint32), H.fr_array(cid, vals))
+
+    a, b, c = csr(cs.a), csr(cs.b), csr(cs.c)          # before squaring: the device indexer squares them itself
+    idx, extra = zm.index(ctx, cid, a, b, c, ni, nv)
+    oidx = OM.index(cs, cid)
+    assert extra == max(nc - nv, 0)
+    assert (idx.num_constraints, idx.num_variables, idx.num_non_zeros) == (oidx["num_constraints"], oidx["num_variables"],
+                                                                            oidx["num_non_zeros"])
+    assert (idx.x_size, idx.h_size, idx.k_size, idx.b_size) == (oidx["dx"].size, oidx["dh"].size, oidx["dk"].size, oidx["db"].size)
+    want = device_index(cid, oidx)
+    for name in "abc":
+        assert np.array_equal(idx.matrices[name].row_ptr, want.matrices[name].row_ptr)
+        assert np.array_equal(idx.matrices[name].col_idx, want.matrices[name].col_idx)
+        assert np.array_equal(idx.matrices[name].coeff, want.matrices[name].coeff)
+        for key, arr in want.stars[name].items():
+            assert np.array_equal(idx.stars[name][key], arr), (name, key)

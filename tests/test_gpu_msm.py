@@ -167,3 +167,34 @@ def test_msm_giant_bucket(ctx, cid, group, precompute):
     want, winf, _ = cref.msm(cid, group, xy, inf, sc)
     assert ginf == winf and np.array_equal(got, want)
     srs.free()
+
+
+@pytest.mark.parametrize("levels", ["0", "1", "2", "7"])
+@pytest.mark.parametrize("cid,group", [(BLS12_381, 1), (BN254, 2)])
+def test_msm_pair_levels_forced(ctx, cid, group, levels, monkeypatch):
+    """The batched-affine pair levels (csrc/msm_affine.cuh) for every level count from "XYZZ only" to
+    "until every bucket holds one point", on inputs that hit each special case of the affine addition:
+    doublings (equal bases, equal scalars), P + (-P), identity partial sums that meet again one level up,
+    identity bases, odd leftovers, empty buckets, and one bucket holding most entries."""
+    monkeypatch.setenv("ZKB_MSM_PAIR_LEVELS", levels)
+    c = CURVES[(cid, group)]
+    r = c.r
+    rng = random.Random(int(levels) * 10 + group)
+    base = H.multiples(cid, group, 24, start=11)
+    k = rng.randrange(r)
+    pts, sc = [], []
+    pts += [base[0]] * 9;                                sc += [k] * 9                    # 9 equal entries: doublings + leftover
+    pts += [base[1], c.neg_affine(base[1])] * 5;         sc += [k] * 10                   # cancelling pairs -> identities
+    pts += [base[2], c.neg_affine(base[2]), base[2]];    sc += [k] * 3                    # identity + P one level up
+    pts += [None, base[3], None];                        sc += [k, k, 5]                  # identity bases
+    pts += base[4:];                                     sc += [rng.randrange(r) for _ in base[4:]]
+    pts += base[4:14];                                   sc += [1] * 10                   # a heavily loaded bucket
+    want = c.to_affine(msm_naive(c, pts, sc))
+    assert gpu_msm(ctx, cid, group, pts, sc, True) == want
+    assert gpu_msm(ctx, cid, group, pts, sc, False) == want
+    # larger random instance against the Pippenger restatement
+    n = 1500 if group == 1 else 400
+    pts = H.multiples(cid, group, n, start=77)
+    sc = [rng.randrange(r) if rng.random() < 0.8 else rng.randrange(3) for _ in range(n)]
+    want = c.to_affine(msm_pippenger(c, pts, sc, FR[cid].bits))
+    assert gpu_msm(ctx, cid, group, pts, sc, True) == want

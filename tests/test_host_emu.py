@@ -45,10 +45,12 @@ def test_field_ops(lib, fid):
         assert run(7, a) == (-a) % p
         assert run(4, a) == a * R % p
         assert run(5, a) == a * Rinv % p
-    for a in vals[1:12] + vals[-5:]:
-        if a:
-            # inv in Montgomery domain: inv(aR) = a^-1 R
-            assert run(3, a * R % p) == pow(a, -1, p) * R % p
+    # inv in Montgomery domain: inv(aR) = a^-1 R (binary extended Euclid), 0 -> 0; powers of two and
+    # p - 2^k walk the round count from its minimum to its maximum
+    bits = p.bit_length()
+    for a in vals + [1 << k for k in range(0, bits - 1, 37)] + [p - (1 << k) for k in range(0, bits - 1, 41)]:
+        a %= p
+        assert run(3, a * R % p) == (pow(a, -1, p) * R % p if a else 0)
 
 
 @pytest.mark.parametrize("cid", [BN254, BLS12_381])
