@@ -10,6 +10,11 @@ import ctypes
 
 import numpy as np
 
+try:                      # device-resident operands are torch tensors (PyTorch = device memory plumbing only)
+    import torch
+except Exception:         # pragma: no cover
+    torch = None
+
 from . import _lib
 from ._lib import BLS12_381, BN254, G1, G2, Csr
 
@@ -31,11 +36,35 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
+def is_dev(a):
+    """device-resident Fr vector: a CUDA torch tensor int64[n, 4] holding the same bytes as the uint64[n, 4] host form"""
+    return torch is not None and isinstance(a, torch.Tensor)
+
+
+def _addr(a):
+    """host or device address: the library copies with cudaMemcpyDefault (unified addressing), so every buffer
+    argument of the vector / polynomial / MSM entry points may live on either side"""
+    if a is None:
+        return None
+    return ctypes.c_void_p(a.data_ptr()) if is_dev(a) else _ptr(a)
+
+
 def _fr(a, what="scalars"):
+    if is_dev(a):
+        if a.dtype != torch.int64 or a.dim() != 2 or a.shape[1] != 4 or not a.is_cuda:
+            raise ValueError("%s must be a CUDA int64[n, 4] tensor" % what)
+        return a.contiguous()
     a = np.ascontiguousarray(a, dtype=np.uint64)
     if a.ndim != 2 or a.shape[1] != 4:
         raise ValueError("%s must be uint64[n, 4]" % what)
     return a
+
+
+def _out_like(a, n):
+    """uninitialised Fr vector of n elements on the same side as `a`"""
+    if is_dev(a):
+        return torch.empty((n, 4), dtype=torch.int64, device=a.device)
+    return np.zeros((n, 4), dtype=np.uint64)
 
 
 class CsrMatrix:
@@ -59,6 +88,14 @@ class CsrMatrix:
     @property
     def nnz(self):
         return len(self.col_idx)
+
+    def to_device(self, device):
+        """resident copy for repeated zkb_spmv calls: same object, the C struct then points at device memory"""
+        t = lambda a, dt: torch.from_numpy(a.view(dt)).to(device)
+        self._dev = (t(self.row_ptr, np.int32), t(self.col_idx, np.int32), t(self.coeff, np.int64))
+        self.c = Csr(len(self.row_ptr) - 1, len(self.col_idx), self._dev[0].data_ptr(), self._dev[1].data_ptr(),
+                     self._dev[2].data_ptr())
+        return self
 
 
 class Srs:
@@ -150,7 +187,7 @@ class Context:
         out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)
         oinf = np.zeros(1, dtype=np.uint8)
         fn = self.lib.zkb_msm_mont if mont else self.lib.zkb_msm
-        self._check(fn(self.handle, srs.handle, base_offset, _ptr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
+        self._check(fn(self.handle, srs.handle, base_offset, _addr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
         return out, bool(oinf[0])
 
     def msm_dev(self, srs, d_scalars_ptr, n, base_offset=0):
@@ -177,10 +214,15 @@ class Context:
     # -- NTT ----------------------------------------------------------------------------------
     def ntt(self, curve, data, log_n, inverse=False, coset=False):
         """In-place transform of uint64[2^log_n, 4] (Montgomery), natural order in and out."""
+        flags = (_lib.NTT_INVERSE if inverse else 0) | (_lib.NTT_COSET if coset else 0)
+        if is_dev(data):
+            if not (data.dtype == torch.int64 and data.is_contiguous() and tuple(data.shape) == (1 << log_n, 4)):
+                raise ValueError("data must be a contiguous CUDA int64[2^log_n, 4] tensor")
+            self._check(self.lib.zkb_ntt_dev(self.handle, curve, ctypes.c_void_p(data.data_ptr()), log_n, flags))
+            return data
         if not (isinstance(data, np.ndarray) and data.dtype == np.uint64 and data.flags.c_contiguous
                 and data.shape == (1 << log_n, 4)):
             raise ValueError("data must be a contiguous uint64[2^log_n, 4] array")
-        flags = (_lib.NTT_INVERSE if inverse else 0) | (_lib.NTT_COSET if coset else 0)
         self._check(self.lib.zkb_ntt(self.handle, curve, _ptr(data), log_n, flags))
         return data
 
@@ -190,8 +232,8 @@ class Context:
 
     def fr_convert(self, curve, a, to_mont):
         a = _fr(a, "elements")
-        out = np.empty_like(a)
-        self._check(self.lib.zkb_fr_convert(self.handle, curve, _ptr(a), _ptr(out), a.shape[0], 1 if to_mont else 0))
+        out = _out_like(a, a.shape[0])
+        self._check(self.lib.zkb_fr_convert(self.handle, curve, _addr(a), _addr(out), a.shape[0], 1 if to_mont else 0))
         return out
 
     # -- polynomial helpers (Marlin) ---------------------------------------------------------------
@@ -200,10 +242,10 @@ class Context:
         p = _fr(p_mont, "polynomial")
         z = np.ascontiguousarray(z_mont, dtype=np.uint64).reshape(4)
         n = p.shape[0]
-        q = np.zeros((max(n - 1, 0), 4), dtype=np.uint64) if want_quotient else None
+        q = _out_like(p, max(n - 1, 0)) if want_quotient else None
         rem = np.zeros(4, dtype=np.uint64)
-        self._check(self.lib.zkb_poly_div_linear(self.handle, curve, _ptr(p), n, _ptr(z),
-                                                 _ptr(q) if (want_quotient and n > 1) else None, _ptr(rem)))
+        self._check(self.lib.zkb_poly_div_linear(self.handle, curve, _addr(p), n, _ptr(z),
+                                                 _addr(q) if (want_quotient and n > 1) else None, _ptr(rem)))
         return q, rem
 
     def poly_eval(self, curve, p_mont, z_mont):
@@ -219,17 +261,18 @@ class Context:
         coeffs = _fr(coeffs_mont, "coefficients")
         if coeffs.shape[0] != k:
             raise ValueError("one coefficient per polynomial")
-        ptrs = (ctypes.c_void_p * max(k, 1))(*[p.ctypes.data for p in polys])
+        ptrs = (ctypes.c_void_p * max(k, 1))(*[p.data_ptr() if is_dev(p) else p.ctypes.data for p in polys])
         lens = (ctypes.c_size_t * max(k, 1))(*[len(p) for p in polys])
         shs = (ctypes.c_size_t * max(k, 1))(*shifts)
-        out = np.zeros((out_len, 4), dtype=np.uint64)
-        self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), _ptr(out), out_len))
+        dev = [p for p in polys if is_dev(p)]
+        out = _out_like(dev[0], out_len) if dev else np.zeros((out_len, 4), dtype=np.uint64)
+        self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), _addr(out), out_len))
         return out
 
     def fr_batch_inverse(self, curve, a_mont):
         a = _fr(a_mont, "elements")
-        out = np.zeros_like(a)
-        self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, _ptr(a), _ptr(out), a.shape[0]))
+        out = _out_like(a, a.shape[0])
+        self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, _addr(a), _addr(out), a.shape[0]))
         return out
 
     VEC_ADD, VEC_SUB, VEC_MUL, VEC_SCALE, VEC_AXPY, VEC_RSUB, VEC_ADDC = range(7)
@@ -241,21 +284,21 @@ class Context:
         if b is not None and b.shape != a.shape:
             raise ValueError("operand shapes differ")
         s = None if s is None else np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
-        out = np.zeros_like(a)
-        self._check(self.lib.zkb_fr_vec_op(self.handle, curve, op, _ptr(a), _ptr(b), _ptr(s), _ptr(out), a.shape[0]))
+        out = _out_like(a, a.shape[0])
+        self._check(self.lib.zkb_fr_vec_op(self.handle, curve, op, _addr(a), _addr(b), _ptr(s), _addr(out), a.shape[0]))
         return out
 
-    def fr_powers(self, curve, base_mont, n, scale_mont=None):
+    def fr_powers(self, curve, base_mont, n, scale_mont=None, device=None):
         base = np.ascontiguousarray(base_mont, dtype=np.uint64).reshape(4)
         sc = None if scale_mont is None else np.ascontiguousarray(scale_mont, dtype=np.uint64).reshape(4)
-        out = np.zeros((n, 4), dtype=np.uint64)
-        self._check(self.lib.zkb_fr_powers(self.handle, curve, _ptr(base), _ptr(sc), _ptr(out), n))
+        out = np.zeros((n, 4), dtype=np.uint64) if device is None else torch.empty((n, 4), dtype=torch.int64, device=device)
+        self._check(self.lib.zkb_fr_powers(self.handle, curve, _ptr(base), _ptr(sc), _addr(out), n))
         return out
 
     def spmv(self, curve, m, x_mont):
         x = _fr(x_mont, "x")
-        y = np.zeros((m.n_rows, 4), dtype=np.uint64)
-        self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), _ptr(x), x.shape[0], _ptr(y)))
+        y = _out_like(x, m.n_rows)
+        self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), _addr(x), x.shape[0], _addr(y)))
         return y
 
     # -- Groth16 ------------------------------------------------------------------------------

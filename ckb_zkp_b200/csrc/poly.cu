@@ -157,22 +157,59 @@ k_fr_powers(Fp<FrP> base, Fp<FrP> scale, Fp<FrP>* __restrict__ out, size_t n) {
   }
 }
 // y[i] = sum_p coeff[p] * x[col[p]] over row i (generic sparse matrix-vector product)
+// y = M x, one thread per row; rows longer than kSpmvLong (Marlin's transposed matrices have one row per
+// VARIABLE, and the constant ONE appears in every other constraint) are deferred to k_spmv_long
+constexpr uint32_t kSpmvLong = 256;
 template <class FrP>
 __global__ void __launch_bounds__(256)
 k_spmv_generic(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx, const Fp<FrP>* __restrict__ coeff,
-               const Fp<FrP>* __restrict__ x, Fp<FrP>* __restrict__ y, uint32_t n_rows) {
+               const Fp<FrP>* __restrict__ x, Fp<FrP>* __restrict__ y, uint32_t n_rows, uint32_t* __restrict__ long_rows,
+               uint32_t* __restrict__ n_long) {
   using Fr = Fp<FrP>;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
+  const uint32_t p0 = row_ptr[i], p1 = row_ptr[i + 1];
+  if (p1 - p0 > kSpmvLong) {
+    long_rows[atomicAdd(n_long, 1u)] = i;
+    return;
+  }
   Fr acc = Fr::zero();
   const Fr one = Fr::one();
-  for (uint32_t p = row_ptr[i]; p < row_ptr[i + 1]; p++) {
+  for (uint32_t p = p0; p < p1; p++) {
     Fr c = ld_vec(&coeff[p]);
     Fr v = ld_vec(&x[col_idx[p]]);
     if (c != one) v = Fr::mul(v, c);
     acc = Fr::add(acc, v);
   }
   st_vec(&y[i], acc);
+}
+// one block per long row: strided partial sums, tree reduction in shared memory
+template <class FrP>
+__global__ void __launch_bounds__(256)
+k_spmv_long(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col_idx, const Fp<FrP>* __restrict__ coeff,
+            const Fp<FrP>* __restrict__ x, Fp<FrP>* __restrict__ y, const uint32_t* __restrict__ long_rows,
+            const uint32_t* __restrict__ n_long) {
+  using Fr = Fp<FrP>;
+  __shared__ Fr sh[256];
+  const Fr one = Fr::one();
+  for (uint32_t j = blockIdx.x; j < *n_long; j += gridDim.x) {
+    const uint32_t i = long_rows[j];
+    Fr acc = Fr::zero();
+    for (uint32_t p = row_ptr[i] + threadIdx.x; p < row_ptr[i + 1]; p += blockDim.x) {
+      Fr c = ld_vec(&coeff[p]);
+      Fr v = ld_vec(&x[col_idx[p]]);
+      if (c != one) v = Fr::mul(v, c);
+      acc = Fr::add(acc, v);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s_ = 128; s_ > 0; s_ >>= 1) {
+      if ((int)threadIdx.x < s_) sh[threadIdx.x] = Fr::add(sh[threadIdx.x], sh[threadIdx.x + s_]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) st_vec(&y[i], sh[0]);
+    __syncthreads();
+  }
 }
 
 template <class FrP>
@@ -187,12 +224,12 @@ static int vec_op_t(zkb_ctx* ctx, cudaStream_t st, int op, const uint64_t* a, co
   ZKB_TRY(ws.alloc(&d_o, n));
   Fr s = Fr::zero();
   if (s_host) memcpy(s.v, s_host, 32);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
-  if (binary) ZKB_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * sizeof(Fr), cudaMemcpyDefault, st));
+  if (binary) ZKB_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * sizeof(Fr), cudaMemcpyDefault, st));
   unsigned blocks = ceil_div(n, 256);
   if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   ZKB_LAUNCH(ctx, (k_fr_vec_op<FrP>), blocks, 256, 0, st, op, (const Fr*)d_a, (const Fr*)d_b, s, d_o, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }
@@ -206,7 +243,7 @@ static int powers_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* base, const u
   memcpy(b.v, base, 32);
   if (scale) memcpy(sc.v, scale, 32);
   ZKB_LAUNCH(ctx, (k_fr_powers<FrP>), ceil_div(ceil_div(n, 32), 128), 128, 0, st, b, sc, d_o, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }
@@ -221,15 +258,23 @@ static int spmv_t(zkb_ctx* ctx, cudaStream_t st, const zkb_csr* m, const uint64_
   ZKB_TRY(ws.alloc(&d_coeff, m->nnz));
   ZKB_TRY(ws.alloc(&d_x, n_cols));
   ZKB_TRY(ws.alloc(&d_y, m->n_rows));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_ptr, m->row_ptr, (m->n_rows + 1) * 4, cudaMemcpyHostToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_ptr, m->row_ptr, (m->n_rows + 1) * 4, cudaMemcpyDefault, st));
   if (m->nnz) {
-    ZKB_CUDA(ctx, cudaMemcpyAsync(d_col, m->col_idx, m->nnz * 4, cudaMemcpyHostToDevice, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(d_coeff, m->coeff_mont, m->nnz * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_col, m->col_idx, m->nnz * 4, cudaMemcpyDefault, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_coeff, m->coeff_mont, m->nnz * sizeof(Fr), cudaMemcpyDefault, st));
   }
-  if (n_cols) ZKB_CUDA(ctx, cudaMemcpyAsync(d_x, x, n_cols * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  if (n_cols) ZKB_CUDA(ctx, cudaMemcpyAsync(d_x, x, n_cols * sizeof(Fr), cudaMemcpyDefault, st));
+  const size_t max_long = m->nnz / kSpmvLong + 1;
+  uint32_t *d_long, *d_n_long;
+  ZKB_TRY(ws.alloc(&d_long, max_long));
+  ZKB_TRY(ws.alloc(&d_n_long, 1));
+  ZKB_CUDA(ctx, cudaMemsetAsync(d_n_long, 0, 4, st));
   ZKB_LAUNCH(ctx, (k_spmv_generic<FrP>), ceil_div(m->n_rows, 256), 256, 0, st, (const uint32_t*)d_ptr, (const uint32_t*)d_col,
-             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (uint32_t)m->n_rows);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(y, d_y, m->n_rows * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (uint32_t)m->n_rows, d_long, d_n_long);
+  unsigned long_blocks = max_long < (size_t)ctx->sm_count * 4 ? (unsigned)max_long : (unsigned)ctx->sm_count * 4;
+  ZKB_LAUNCH(ctx, (k_spmv_long<FrP>), long_blocks, 256, 0, st, (const uint32_t*)d_ptr, (const uint32_t*)d_col,
+             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (const uint32_t*)d_long, (const uint32_t*)d_n_long);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(y, d_y, m->n_rows * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }
@@ -296,7 +341,7 @@ static int lincomb_t(zkb_ctx* ctx, cudaStream_t st, size_t k, const uint64_t* co
   for (size_t j = 0; j < k; j++) {
     Fr* d;
     ZKB_TRY(ws.alloc(&d, lens[j]));
-    if (lens[j]) ZKB_CUDA(ctx, cudaMemcpyAsync(d, polys[j], lens[j] * sizeof(Fr), cudaMemcpyHostToDevice, st));
+    if (lens[j]) ZKB_CUDA(ctx, cudaMemcpyAsync(d, polys[j], lens[j] * sizeof(Fr), cudaMemcpyDefault, st));
     h.poly[j] = d;
     h.len[j] = lens[j];
     h.shift[j] = shifts ? shifts[j] : 0;
@@ -306,11 +351,11 @@ static int lincomb_t(zkb_ctx* ctx, cudaStream_t st, size_t k, const uint64_t* co
   Fr* d_out;
   ZKB_TRY(ws.alloc(&d_args, 1));
   ZKB_TRY(ws.alloc(&d_out, out_len));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_args, &h, sizeof h, cudaMemcpyHostToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_args, &h, sizeof h, cudaMemcpyDefault, st));
   unsigned blocks = ceil_div(out_len, 256);
   if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   ZKB_LAUNCH(ctx, (k_poly_lincomb<FrP>), blocks, 256, 0, st, (const LincombArgs<FrP>*)d_args, d_out, out_len);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_len * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_len * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));      // h lives on this stack frame
   return ZKB_OK;
 }
@@ -323,9 +368,9 @@ static int batch_inverse_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, ui
   ZKB_TRY(ws.alloc(&d_in, n));
   ZKB_TRY(ws.alloc(&d_out, n));
   ZKB_TRY(ws.alloc(&d_scr, n));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyHostToDevice, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_LAUNCH(ctx, (k_batch_inverse<FrP>), ceil_div(ceil_div(n, kPolyChunk), 128), 128, 0, st, (const Fr*)d_in, d_out, d_scr, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }
@@ -348,10 +393,10 @@ int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t 
   ZKB_TRY(ws.alloc(&d_p, n * 8));
   ZKB_TRY(ws.alloc(&d_q, n * 8));
   ZKB_TRY(ws.alloc(&d_rem, 8));
-  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(d_p, p_mont, n * 32, cudaMemcpyHostToDevice, st));
+  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(d_p, p_mont, n * 32, cudaMemcpyDefault, st));
   ZKB_TRY(poly_div_linear_dev(ctx, st, curve, d_p, n, z_mont, q_mont ? d_q : nullptr, d_rem));
-  if (q_mont && n > 1) ZKB_CUDA(ctx, cudaMemcpyAsync(q_mont, d_q, (n - 1) * 32, cudaMemcpyDeviceToHost, st));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(rem_mont, d_rem, 32, cudaMemcpyDeviceToHost, st));
+  if (q_mont && n > 1) ZKB_CUDA(ctx, cudaMemcpyAsync(q_mont, d_q, (n - 1) * 32, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(rem_mont, d_rem, 32, cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;
 }

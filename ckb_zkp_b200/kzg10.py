@@ -13,7 +13,7 @@ Polynomials are uint64[n, 4] Montgomery coefficient arrays, low degree first.
 import numpy as np
 
 from . import _lib
-from .backend import point_words
+from .backend import is_dev, point_words, torch
 from .r1cs import ints_to_limbs
 
 FR_MODULUS = {
@@ -50,13 +50,20 @@ class MissingPolynomial(KzgError):
     pass
 
 
+def _nonzero_rows(p):
+    """indices of the non-zero coefficients of a host (numpy) or resident (CUDA tensor) polynomial"""
+    if is_dev(p):
+        return torch.nonzero((p != 0).any(dim=1)).reshape(-1)
+    return np.flatnonzero(p.any(axis=1))
+
+
 def _degree(p):
-    nz = np.flatnonzero(p.any(axis=1))
+    nz = _nonzero_rows(p)
     return int(nz[-1]) if len(nz) else 0
 
 
 def _leading_zeros(p):
-    nz = np.flatnonzero(p.any(axis=1))
+    nz = _nonzero_rows(p)
     return int(nz[0]) if len(nz) else len(p)
 
 
@@ -97,7 +104,9 @@ class LabeledPolynomial:
     """data_structures.rs:218-263"""
 
     def __init__(self, label, coeffs_mont, degree_bound=None, hiding_bound=None):
-        self.label, self.coeffs = label, np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4)
+        self.label = label
+        self.coeffs = (coeffs_mont.contiguous() if is_dev(coeffs_mont)
+                       else np.ascontiguousarray(coeffs_mont, dtype=np.uint64).reshape(-1, 4))
         self.degree_bound, self.hiding_bound = degree_bound, hiding_bound
 
 
@@ -187,7 +196,7 @@ def pc_open(ck, polynomials, point_mont, opening_challenge, randomnesses):
             rpolys.append(rand.blinding); rcoeffs.append(challenge)
         if P.degree_bound is not None:
             sc = challenge * opening_challenge % mod
-            if P.coeffs.any():                                       # shift_polynomial (:241-250)
+            if bool(P.coeffs.any()):                                 # shift_polynomial (:241-250)
                 polys.append(P.coeffs); shifts.append(ck.supported_degree - P.degree_bound); coeffs.append(sc)
             if shifted_rand is not None and len(shifted_rand.blinding):
                 rpolys.append(shifted_rand.blinding); rcoeffs.append(sc)

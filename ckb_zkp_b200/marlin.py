@@ -21,7 +21,7 @@ arrays, low degree first, trimmed like ark-poly's DensePolynomial.
 import numpy as np
 
 from . import _lib
-from .backend import CsrMatrix
+from .backend import CsrMatrix, is_dev, torch
 from .r1cs import ints_to_limbs
 
 FR_MODULUS = {
@@ -84,12 +84,22 @@ class Field:
 
 
 def trim(p):
+    """drop leading (high-degree) zero coefficients, like DensePolynomial::from_coefficients_vec"""
+    if is_dev(p):
+        nz = torch.nonzero((p != 0).any(dim=1))
+        return p[:int(nz[-1]) + 1] if len(nz) else p[:0]
     nz = np.flatnonzero(p.any(axis=1))
     return p[:int(nz[-1]) + 1] if len(nz) else p[:0]
 
 
 def pad(p, n):
     """a fresh array of exactly n coefficients (always a copy: the transforms work in place)"""
+    if is_dev(p):
+        if len(p) >= n:
+            return p[:n].clone()
+        out = torch.zeros((n, 4), dtype=torch.int64, device=p.device)
+        out[:len(p)] = p
+        return out
     if len(p) >= n:
         return p[:n].copy()
     out = np.zeros((n, 4), dtype=np.uint64)
@@ -97,11 +107,56 @@ def pad(p, n):
     return out
 
 
+def contig(a):
+    return a.contiguous() if is_dev(a) else np.ascontiguousarray(a)
+
+
+def to_host(a):
+    """uint64[n, 4] numpy copy of a host or device Fr vector"""
+    return a.cpu().numpy().view(np.uint64) if is_dev(a) else np.asarray(a)
+
+
 class Ops:
     """device-backed polynomial / vector arithmetic for one (ctx, curve)"""
 
-    def __init__(self, ctx, curve):
+    def __init__(self, ctx, curve, resident=False):
+        """resident=True keeps every vector in HBM (CUDA int64[n, 4] tensors): the primitives then exchange device
+        pointers and only the few scalars that feed the transcript travel to the host.  torch's current stream is
+        pointed at the library's stream so tensor glue (slicing, concatenation, zero fill) and kernels stay ordered."""
         self.ctx, self.curve, self.f = ctx, curve, Field(curve)
+        self.device = None
+        if resident:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.stream, device=self.device))
+
+    # array plumbing on whichever side the vectors live
+    def zeros(self, n):
+        if self.device is not None:
+            return torch.zeros((n, 4), dtype=torch.int64, device=self.device)
+        return np.zeros((n, 4), dtype=np.uint64)
+
+    def put(self, a):
+        """host uint64[n, 4] -> the side this Ops works on"""
+        if self.device is None or is_dev(a):
+            return a
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(self.device)
+
+    def cat(self, parts):
+        return torch.cat(parts) if is_dev(parts[0]) else np.concatenate(parts)
+
+    def take(self, a, idx):
+        """a[idx] for a host index array"""
+        if is_dev(a):
+            return a[torch.from_numpy(np.ascontiguousarray(idx, dtype=np.int64)).to(a.device)]
+        return np.ascontiguousarray(a[idx])
+
+    def zero_rows(self, a, mask):
+        """a[mask] = 0 for a host boolean mask"""
+        if is_dev(a):
+            a[torch.from_numpy(mask).to(a.device)] = 0
+        else:
+            a[mask] = 0
+        return a
 
     def _v(self, op, a, b=None, s=None):
         return self.ctx.fr_vec_op(self.curve, op, a, b, None if s is None else self.f.mont(s))
@@ -127,7 +182,7 @@ class Ops:
 
     def elements(self, size):
         """domain.elements(): w^i"""
-        return self.ctx.fr_powers(self.curve, self.f.mont(self.f.root_of_unity(size)), size)
+        return self.ctx.fr_powers(self.curve, self.f.mont(self.f.root_of_unity(size)), size, device=self.device)
 
     def poly_add(self, a, b):
         n = max(len(a), len(b))
@@ -148,22 +203,25 @@ class Ops:
         """DensePolynomial::divide_by_vanishing_poly for x^n - 1 -> (quotient, remainder)"""
         if len(p) < n:
             return p[:0], trim(p)
-        q = p[n:].copy()           # a copy: the accumulation below must not alias the tails it reads
-        for i in range(1, len(p) // n):
-            tail = p[n * (i + 1):]
-            if len(tail):
-                q[:len(tail)] = self.add(np.ascontiguousarray(q[:len(tail)]), np.ascontiguousarray(tail))
-        r = p[:n].copy()
+        # q[j] = sum_{i >= 1} p[j + i n]: a suffix sum with stride n, by doubling (log2(len / n) vector additions
+        # instead of len / n -- the division of w by v_X has n = |X| = 2 and len = |H|)
+        q = pad(p[n:], len(p) - n)
+        s = n
+        while s < len(q):
+            m = len(q) - s
+            q[:m] = self.add(contig(q[:m]), contig(q[s:]))
+            s *= 2
+        r = pad(p[:n], n)
         k = min(n, len(q))
         if k:
-            r[:k] = self.add(np.ascontiguousarray(r[:k]), np.ascontiguousarray(q[:k]))
+            r[:k] = self.add(contig(r[:k]), contig(q[:k]))
         return trim(q), trim(r)
 
     def mul_by_vanishing_poly(self, p, n):
-        out = np.zeros((len(p) + n, 4), dtype=np.uint64)
+        out = self.zeros(len(p) + n)
         out[n:] = p
         if len(p):
-            out[:len(p)] = self.sub(np.ascontiguousarray(out[:len(p)]), np.ascontiguousarray(p))
+            out[:len(p)] = self.sub(contig(out[:len(p)]), contig(p))
         return trim(out)
 
     def add_const_terms(self, p, terms):
@@ -171,7 +229,8 @@ class Ops:
         n = max([len(p)] + [k + 1 for k, _ in terms])
         out = pad(p, n)
         for k, c in terms:
-            out[k] = self.f.mont(self.f.to_int(out[k]) + c)
+            cur = self.f.to_int(to_host(out[k:k + 1])[0])
+            out[k:k + 1] = self.put(self.f.mont(cur + c).reshape(1, 4))
         return trim(out)
 
     def batch_evals(self, size, x):
@@ -205,6 +264,19 @@ class Index:
             ptr = np.zeros(self.h_size + 1, dtype=np.uint32)
             np.cumsum(np.bincount(k, minlength=self.h_size), out=ptr[1:])
             self.transposed[name] = CsrMatrix(ptr, rows[order].astype(np.uint32), m.coeff[order])
+        self.resident = False
+
+    def make_resident(self, ops):
+        """move the matrices and the evaluation tables into HBM once (the index outlives many proofs)"""
+        if self.resident:
+            return
+        for m in list(self.matrices.values()) + list(self.transposed.values()):
+            m.to_device(ops.device)
+        for star in self.stars.values():
+            for key in ("row_evals_on_k", "col_evals_on_k", "val_evals_on_k", "row_evals_on_b", "col_evals_on_b",
+                        "val_evals_on_b", "row_col_evals_on_b"):
+                star[key] = ops.put(star[key])
+        self.resident = True
 
 
 def make_matrices_square(mats, num_variables):
@@ -312,16 +384,20 @@ class ProverState:
     pass
 
 
-def prover_init(ctx, index, formatted_input_mont, witness_mont):
+def prover_init(ctx, index, formatted_input_mont, witness_mont, resident=False):
     """prover.rs:86-147 after synthesis and make_matrices_square: formatted_input = [one, inputs..],
-    witness = aux assignment (+ padding variables)."""
+    witness = aux assignment (+ padding variables).  resident=True keeps the whole round state in HBM
+    (see Ops); the oracles returned by the rounds are then CUDA tensors."""
     ni, nw = len(formatted_input_mont), len(witness_mont)
     if index.num_constraints != index.matrices["a"].n_rows or index.num_constraints != ni + nw:
         raise InstanceDoesNotMatchIndex()
     st = ProverState()
-    st.ctx, st.index, st.ops = ctx, index, Ops(ctx, index.curve)
-    st.x, st.w = np.ascontiguousarray(formatted_input_mont), np.ascontiguousarray(witness_mont)
-    z = np.concatenate([st.x, st.w])
+    st.ctx, st.index, st.ops = ctx, index, Ops(ctx, index.curve, resident)
+    o = st.ops
+    if resident:
+        index.make_resident(o)
+    st.x, st.w = o.put(np.ascontiguousarray(formatted_input_mont)), o.put(np.ascontiguousarray(witness_mont))
+    z = o.cat([st.x, st.w])
     st.z_a = ctx.spmv(index.curve, index.matrices["a"], z)
     st.z_b = ctx.spmv(index.curve, index.matrices["b"], z)
     st.zk_bound = 1
@@ -341,11 +417,10 @@ def prover_first_round(st, rng):
     if H > X:
         w_ext = pad(st.w, H - X)
         src = np.where(i % ratio == 0, 0, i - i // ratio - 1)
-        gathered = np.ascontiguousarray(w_ext[src])
+        gathered = o.take(w_ext, src)
     else:
-        gathered = np.zeros((H, 4), dtype=np.uint64)
-    w_minus_x = o.sub(gathered, x_evals_on_h)
-    w_minus_x[i % ratio == 0] = 0
+        gathered = o.zeros(H)
+    w_minus_x = o.zero_rows(o.sub(gathered, x_evals_on_h), i % ratio == 0)
 
     def blind(poly):                                                 # + DensePolynomial::rand(zk_bound - 1) * v_H
         c = rng.randrange(p)
@@ -364,12 +439,12 @@ def prover_first_round(st, rng):
         heads = np.ascontiguousarray(mask_canon[0::H])
         sigma = sum(int.from_bytes(h.tobytes(), "little") for h in heads) % p
         mask_canon[0] = ints_to_limbs([(int.from_bytes(mask_canon[0].tobytes(), "little") - sigma) % p])[0]
-        mask_poly = trim(st.ctx.fr_convert(idx.curve, mask_canon, to_mont=True))
+        mask_poly = trim(st.ctx.fr_convert(idx.curve, o.put(mask_canon), to_mont=True))
     else:
         mask_ints = [rng.randrange(p) for _ in range(mask_degree + 1)]
         sigma = sum(mask_ints[k] for k in range(0, len(mask_ints), H)) % p     # remainder coefficient 0 mod (x^H - 1)
         mask_ints[0] = (mask_ints[0] - sigma) % p
-        mask_poly = trim(st.ctx.fr_convert(idx.curve, ints_to_limbs(mask_ints), to_mont=True))
+        mask_poly = trim(st.ctx.fr_convert(idx.curve, o.put(ints_to_limbs(mask_ints)), to_mont=True))
     st.x_poly, st.w_poly, st.z_a_poly, st.z_b_poly, st.mask_poly = x_poly, w_poly, z_a_poly, z_b_poly, mask_poly
     # (label, polynomial, degree_bound, hiding_bound) as in ProverFirstOracles
     return [("w", w_poly, None, 1), ("z_a", z_a_poly, None, 1), ("z_b", z_b_poly, None, 1), ("mask", mask_poly, None, None)]
@@ -383,20 +458,19 @@ def prover_second_round(st, alpha, eta_a, eta_b, eta_c):
     m = o.scale(o.poly_mul(za, zb), eta_c)
     k = min(len(m), len(za), len(zb))
     if k:
-        low = o.axpy(o.axpy(np.ascontiguousarray(m[:k]), eta_a, np.ascontiguousarray(za[:k])), eta_b,
-                     np.ascontiguousarray(zb[:k]))
-        m = np.concatenate([low, m[k:]])
+        low = o.axpy(o.axpy(contig(m[:k]), eta_a, contig(za[:k])), eta_b, contig(zb[:k]))
+        m = o.cat([low, m[k:]])
     m_poly = trim(m)
     r_alpha_evals = o.batch_evals(H, alpha)
     r_alpha_poly = trim(o.ifft(r_alpha_evals, H))
-    t_evals = np.zeros((H, 4), dtype=np.uint64)
+    t_evals = o.zeros(H)
     for name, eta in (("a", eta_a), ("b", eta_b), ("c", eta_c)):
         t_evals = o.axpy(t_evals, eta, st.ctx.spmv(idx.curve, idx.transposed[name], r_alpha_evals))
     t_poly = trim(o.ifft(t_evals, H))
     z_poly = o.mul_by_vanishing_poly(st.w_poly, X)
     k = min(len(z_poly), len(st.x_poly))
     if k:
-        z_poly = np.concatenate([o.add(np.ascontiguousarray(z_poly[:k]), np.ascontiguousarray(st.x_poly[:k])), z_poly[k:]])
+        z_poly = o.cat([o.add(contig(z_poly[:k]), contig(st.x_poly[:k])), z_poly[k:]])
     size = domain_size(max(len(st.mask_poly), len(r_alpha_poly) + len(m_poly), len(t_poly) + len(z_poly)))
     ev = o.sub(o.mul(o.fft(r_alpha_poly, size), o.fft(m_poly, size)), o.mul(o.fft(t_poly, size), o.fft(z_poly, size)))
     q1 = o.poly_add(st.mask_poly, trim(o.ifft(ev, size)))
@@ -415,7 +489,7 @@ def prover_third_round(st, beta):
     vv = o.f.vanishing_at(H, alpha) * o.f.vanishing_at(H, beta) % p
     stars = [idx.stars[n] for n in "abc"]
     etas = [eta_a, eta_b, eta_c]
-    t_k = np.zeros((K, 4), dtype=np.uint64)
+    t_k = o.zeros(K)
     for s, eta in zip(stars, etas):
         inv = o.inv(o.mul(o.rsub(beta, s["row_evals_on_k"]), o.rsub(alpha, s["col_evals_on_k"])))
         t_k = o.axpy(t_k, eta, o.mul(s["val_evals_on_k"], inv))
@@ -428,7 +502,7 @@ def prover_third_round(st, beta):
         d = o.axpy(d, -beta % p, s["col_evals_on_b"])
         den.append(o.addc(d, alpha * beta % p))
     pairs = [(1, 2), (2, 0), (0, 1)]
-    a_evals = np.zeros((B, 4), dtype=np.uint64)
+    a_evals = o.zeros(B)
     for s, eta, (u, v) in zip(stars, etas, pairs):
         a_evals = o.axpy(a_evals, eta, o.mul(s["val_evals_on_b"], o.mul(den[u], den[v])))
     a_poly = trim(o.ifft(o.scale(a_evals, vv), B))

@@ -34,7 +34,7 @@ class MockContext:
         data[:] = H.fr_array(curve, fn(vals))
         return data
 
-    def fr_powers(self, curve, base_mont, n, scale_mont=None):
+    def fr_powers(self, curve, base_mont, n, scale_mont=None, device=None):
         p = FR[curve].p
         b = self._ints(curve, base_mont)[0]
         s = self._ints(curve, scale_mont)[0] if scale_mont is not None else 1

@@ -76,9 +76,10 @@ def outside(domain, rng, p):
             return t
 
 
+@pytest.mark.parametrize("resident", [False, True])      # host-buffer API / round state resident in HBM
 @pytest.mark.parametrize("cid,build", [(BLS12_381, mini), (BN254, lambda cs: mimc(cs, 12)), (BN254, lambda cs: mimc(cs, 60)),
                                        (BN254, lambda cs: mimc(cs, 1000))])   # |H| = 2^10, |K| = 2^11, |B| = 2^13
-def test_ahp_rounds_match_oracle(ctx, cid, build):
+def test_ahp_rounds_match_oracle(ctx, cid, build, resident):
     fr = FR[cid]
     p = fr.p
     rng = random.Random(31)
@@ -88,8 +89,8 @@ def test_ahp_rounds_match_oracle(ctx, cid, build):
     ost = OM.prover_init(oidx, cs)
     idx = device_index(cid, oidx)
     assert (idx.x_size, idx.h_size, idx.k_size, idx.b_size) == (oidx["dx"].size, oidx["dh"].size, oidx["dk"].size, oidx["db"].size)
-    st = zm.prover_init(ctx, idx, H.fr_array(cid, cs.input), H.fr_array(cid, cs.witness))
-    assert H.fr_ints(cid, st.z_a) == ost["z_a"] and H.fr_ints(cid, st.z_b) == ost["z_b"]
+    st = zm.prover_init(ctx, idx, H.fr_array(cid, cs.input), H.fr_array(cid, cs.witness), resident=resident)
+    assert H.fr_ints(cid, zm.to_host(st.z_a)) == ost["z_a"] and H.fr_ints(cid, zm.to_host(st.z_b)) == ost["z_b"]
 
     Hs = oidx["dh"].size
     draws = [rng.randrange(p) for _ in range(3 + 3 * Hs)]
@@ -103,7 +104,7 @@ def test_ahp_rounds_match_oracle(ctx, cid, build):
     o3 = OM.prover_third_round(ost, beta)
     g3 = zm.prover_third_round(st, beta)
     want = {**o1, **o2, **o3}
-    got = {label: H.fr_ints(cid, poly) for label, poly, _, _ in g1 + g2 + g3}
+    got = {label: H.fr_ints(cid, zm.to_host(poly)) for label, poly, _, _ in g1 + g2 + g3}
     for label in ("w", "z_a", "z_b", "mask", "t", "g_1", "h_1", "g_2", "h_2"):
         assert got[label] == want[label], label
     bounds = {label: (db, hb) for label, _, db, hb in g1 + g2 + g3}
@@ -113,7 +114,8 @@ def test_ahp_rounds_match_oracle(ctx, cid, build):
     assert OM.verifier_equality_check(oidx, cs.input[1:], got, alpha, *etas, beta, gamma)
 
 
-def test_marlin_commit_and_open_flow(ctx):
+@pytest.mark.parametrize("resident", [False, True])
+def test_marlin_commit_and_open_flow(ctx, resident):
     """marlin/src/lib.rs:97-181 with the challenges supplied: three rounds of PC::commit over the AHP
     oracles, evaluations at beta / gamma, PC::batch_open -- commitments and opening proofs compared with
     the oracle's KZG layer, and every opening checked in the exponent (PC::check)."""
@@ -125,7 +127,7 @@ def test_marlin_commit_and_open_flow(ctx):
     mimc(cs, 12)
     oidx = OM.index(cs, cid)
     idx = device_index(cid, oidx)
-    st = zm.prover_init(ctx, idx, H.fr_array(cid, cs.input), H.fr_array(cid, cs.witness))
+    st = zm.prover_init(ctx, idx, H.fr_array(cid, cs.input), H.fr_array(cid, cs.witness), resident=resident)
     Hs, Ks = idx.h_size, idx.k_size
     max_degree = max(3 * Hs + 2 - 1, 3 * Ks - 3)                              # AHP::max_degree (ahp/mod.rs:66-84)
     pp = OK.setup(cid, max_degree, rng.randrange(p), g_scalar=rng.randrange(1, p), gamma=rng.randrange(1, p))
@@ -148,7 +150,7 @@ def test_marlin_commit_and_open_flow(ctx):
             b1 = [rng.randrange(p) for _ in range(2)] if hb else None
             b2 = [rng.randrange(p) for _ in range(2)] if (hb and db is not None) else None
             blinds += (b1 or []) + (b2 or [])
-            opolys.append({"label": label, "coeffs": H.fr_ints(cid, poly), "degree_bound": db, "blinding": b1,
+            opolys.append({"label": label, "coeffs": H.fr_ints(cid, zm.to_host(poly)), "degree_bound": db, "blinding": b1,
                            "shifted_blinding": b2})
         comms, rands = zk.pc_commit(ck, polys, ReplayRng(blinds))              # lib.rs:109-110,117-118,124-125
         labeled += polys
@@ -167,7 +169,7 @@ def test_marlin_commit_and_open_flow(ctx):
     f = zm.Field(cid)
     for label, point in query:
         ev = f.to_int(ctx.poly_eval(cid, by_label[label].coeffs, f.mont(point)))
-        assert ev == OK.poly_eval(H.fr_ints(cid, by_label[label].coeffs), point, p)
+        assert ev == OK.poly_eval(H.fr_ints(cid, zm.to_host(by_label[label].coeffs)), point, p)
     opening_challenge = rng.randrange(1 << 128)                               # u128::rand (lib.rs:158)
     proofs = zk.pc_batch_open(ck, labeled, query, opening_challenge, all_rands)
     o_by_label = {P["label"]: P for P in opolys}
@@ -237,3 +239,34 @@ def test_gpu_indexer_matches_oracle(ctx, cid, build):
         assert np.array_equal(idx.matrices[name].coeff, want.matrices[name].coeff)
         for key, arr in want.stars[name].items():
             assert np.array_equal(idx.stars[name][key], arr), (name, key)
+
+
+@pytest.mark.parametrize("cid", [BN254, BLS12_381])
+@pytest.mark.parametrize("resident", [False, True])
+def test_spmv_long_and_empty_rows(ctx, cid, resident):
+    """zkb_spmv (ahp/prover.rs:110-123, 259-269) with the row shapes of Marlin's transposed matrices: one row far
+    longer than the per-thread limit (the ONE variable), empty rows, coefficient 1 fast path, duplicate columns."""
+    fr = FR[cid]
+    p = fr.p
+    rng = random.Random(cid + 17)
+    n_cols = 700
+    rows = [[(rng.randrange(p), rng.randrange(n_cols)) for _ in range(1500)],        # long row -> block reduction
+            [], [(1, 5), (1, 5), (p - 1, 6)], [], [(rng.randrange(p), 699)],
+            [(rng.randrange(p), rng.randrange(n_cols)) for _ in range(257)],          # just above the limit
+            [(rng.randrange(p), rng.randrange(n_cols)) for _ in range(256)]]          # exactly at the limit
+    x = [rng.randrange(p) for _ in range(n_cols)]
+    ptr, cols, vals = [0], [], []
+    for row in rows:
+        for co, j in row:
+            cols.append(j)
+            vals.append(co)
+        ptr.append(len(cols))
+    m = CsrMatrix(np.asarray(ptr, dtype=np.uint32), np.asarray(cols, dtype=np.uint32), H.fr_array(cid, vals))
+    xv = H.fr_array(cid, x)
+    if resident:
+        import torch
+        dev = torch.device("cuda", 0)
+        m.to_device(dev)
+        xv = torch.from_numpy(xv.view(np.int64)).to(dev)
+    got = H.fr_ints(cid, zm.to_host(ctx.spmv(cid, m, xv)))
+    assert got == [sum(co * x[j] for co, j in row) % p for row in rows]

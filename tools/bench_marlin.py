@@ -8,8 +8,9 @@ Follows zkp_marlin::create_random_proof (marlin/src/lib.rs:97-181): prover_init,
 by PC::commit, the evaluations at beta / gamma and PC::batch_open.  The verifier challenges and the blinding
 draws come from a seeded generator (the Fiat-Shamir byte stream needs the Rust host); index and
 committer key are built once outside the timed region, like `index()` / `universal_setup()` in the reference.
-Every field / group operation runs on the GPU; between primitives the polynomials travel through host arrays
-(one H2D / D2H per primitive), so this is the end-to-end number of the host-buffer API, not a resident one.
+Every field / group operation runs on the GPU and the round state (assignment, oracles, index tables, committer
+key) stays resident in HBM; only the scalars that feed the transcript (evaluations, commitments) reach the host.
+`--host-buffers` times the same flow with host arrays between primitives (one H2D / D2H per primitive).
 Full-size check (on by default): the committer key's trapdoor is known here, so every commitment must equal
 (p(beta) + gamma * r(beta)) * G (shifted ones: beta^shift * p(beta) ...) -- evaluated on the GPU and compared
 with the MSM results; the AHP identities themselves are checked against the oracle at small sizes in
@@ -34,9 +35,34 @@ ap.add_argument("--log-h", type=int, default=18)
 ap.add_argument("--curve", type=int, default=_lib.BN254)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--no-verify", action="store_true")
+ap.add_argument("--host-buffers", action="store_true", help="round state in host arrays (one H2D/D2H per primitive)")
 a = ap.parse_args()
 
 ctx = Context(0)
+
+# per-primitive wall-clock accounting (host-buffer API: includes the copies of each call)
+PROF = {}
+for _name in ("msm", "ntt", "fr_vec_op", "fr_batch_inverse", "spmv", "fr_powers", "fr_convert", "poly_div_linear", "poly_lincomb",
+              "poly_eval", "fixed_base_mul", "srs_upload"):
+    def _wrap(fn, key):
+        def inner(*args, **kw):
+            t = time.perf_counter()
+            try:
+                return fn(*args, **kw)
+            finally:
+                c = PROF.setdefault(key, [0, 0.0])
+                c[0] += 1
+                c[1] += time.perf_counter() - t
+        return inner
+    setattr(ctx, _name, _wrap(getattr(ctx, _name), _name))
+
+
+def prof_report(tag, total):
+    acc = sum(v[1] for v in PROF.values())
+    print("%s: %.3f s total, %.3f s inside backend calls; %s" % (tag, total, acc, ", ".join(
+        "%s %dx %.3fs" % (k, v[0], v[1]) for k, v in sorted(PROF.items(), key=lambda kv: -kv[1][1]))), file=sys.stderr, flush=True)
+    PROF.clear()
+
 curve = a.curve
 f = zm.Field(curve)
 p = f.p
@@ -48,7 +74,7 @@ ni, nv = inst.n_inputs, inst.n_inputs + inst.n_aux
 index, extra = zm.index(ctx, curve, A, B, C, ni, nv)
 assert extra == 0 and index.h_size == 1 << a.log_h
 index_s = time.perf_counter() - t0
-print('index %.2f s' % index_s, file=sys.stderr, flush=True)
+prof_report('index', index_s)
 
 # ---- committer key: powers beta^i * G and gamma * beta^i * G (kzg10.rs:27-72), exponents known -> checkable
 t0 = time.perf_counter()
@@ -71,7 +97,7 @@ def power_points(scale):
 
 ck = zk.CommitterKey(ctx, curve, power_points(1), power_points(gamma_srs), max_degree)
 setup_s = time.perf_counter() - t0
-print('committer key %.2f s' % setup_s, file=sys.stderr, flush=True)
+prof_report('committer key', setup_s)
 
 
 class Draws:
@@ -99,7 +125,7 @@ def outside_h(r):
 def prove(seed):
     """lib.rs:97-181 with seeded challenges; returns (commitments, evaluations, opening proofs, polynomials)"""
     zk_rng, ch = Draws(seed), random.Random(seed + 1)
-    st = zm.prover_init(ctx, index, z_mont[:ni], z_mont[ni:])
+    st = zm.prover_init(ctx, index, z_mont[:ni], z_mont[ni:], resident=not a.host_buffers)
     labeled, comms, rands = [], [], []
 
     def commit(round_polys):
@@ -126,7 +152,7 @@ def prove(seed):
 
 t0 = time.perf_counter()
 prove(100)                                   # warm-up: domains, pools
-print('warm-up prove %.3f s' % (time.perf_counter() - t0), file=sys.stderr, flush=True)
+prof_report('warm-up prove', time.perf_counter() - t0)
 launches0 = ctx.launch_count
 times = []
 for i in range(a.steps):
@@ -134,7 +160,7 @@ for i in range(a.steps):
     out = prove(200 + i)
     ctx.sync()
     times.append(time.perf_counter() - t0)
-    print('prove %.3f s' % times[-1], file=sys.stderr, flush=True)
+    prof_report('prove', times[-1])
 launches = (ctx.launch_count - launches0) // a.steps
 sec = sum(times) / len(times)
 
@@ -164,8 +190,9 @@ line = {"metric": "marlin_proofs_per_sec_bn254_2e%d_constraints" % a.log_h, "val
                                "committer key %d G1 powers (BASELINE configs[4] on one GPU)"
                                % ("BN254" if curve == _lib.BN254 else "BLS12-381", n, a.log_h, Ks.bit_length() - 1,
                                   index.b_size.bit_length() - 1, max_degree + 1),
-                   "timing": "wall clock around create_random_proof's body through the host-buffer API (every primitive "
-                             "copies its operands H2D and its result D2H); challenges and blinding draws seeded",
+                   "timing": "wall clock around create_random_proof's body, assignment uploaded inside the timed region; "
+                             "round state %s; challenges and blinding draws seeded"
+                             % ("in host arrays between primitives" if a.host_buffers else "resident in HBM"),
                    "commitments": len(out[0]), "openings": len(out[2])},
         "gpu_launches": launches, "index_s": round(index_s, 2), "setup_s": round(setup_s, 2), "verified": checked}
 print(json.dumps(line))
