@@ -158,7 +158,13 @@ int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_
 /* out[i] = into_repr(in[i]) (mode 0) or from_repr(in[i]) (mode 1) */
 int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode);
 
-/* ---- polynomial helpers of the Marlin prover (all Fr data Montgomery, host buffers) ----------
+/* ---- polynomial helpers of the Marlin prover (all Fr data Montgomery) -------------------------
+ * Buffer arguments of this group, of zkb_fr_vec_op / zkb_fr_batch_inverse / zkb_fr_powers / zkb_spmv
+ * (including the arrays a zkb_csr points at), of zkb_fr_convert and the scalar array of zkb_msm /
+ * zkb_msm_mont may be HOST or DEVICE memory: the library moves them with cudaMemcpyDefault (unified
+ * addressing), so a caller that keeps the round state resident in HBM passes device pointers and
+ * pays a device-to-device copy instead of two PCIe transfers.  Scalars (z, coefficients) and
+ * results that feed the transcript (remainders, points) are host memory.
  * q = p / (x - z) and rem = p(z): KZG10::compute_witness_polynomial (marlin/src/pc/kzg10.rs:211-226)
  * and LabeledPolynomial::evaluate (marlin/src/lib.rs:147-156).  p has n coefficients (low degree
  * first), q receives n - 1 (may be NULL to evaluate only). */
