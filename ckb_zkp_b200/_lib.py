@@ -35,6 +35,7 @@ SIGNATURES = {
     "zkb_stream": (c_void_p, [c_void_p]),
     "zkb_sync": (c_int, [c_void_p]),
     "zkb_launch_count": (c_u64, [c_void_p]),
+    "zkb_set_serial": (c_int, [c_void_p, c_int]),
     "zkb_prof_enable": (c_int, [c_void_p, c_int]),
     "zkb_prof_read": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64),
                               ctypes.POINTER(ctypes.c_double)]),

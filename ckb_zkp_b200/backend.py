@@ -157,6 +157,9 @@ class Context:
     def launch_count(self):
         return int(self.lib.zkb_launch_count(self.handle))
 
+    def set_serial(self, on):
+        self._check(self.lib.zkb_set_serial(self.handle, 1 if on else 0))
+
     def prof_enable(self, on):
         self._check(self.lib.zkb_prof_enable(self.handle, 1 if on else 0))
 

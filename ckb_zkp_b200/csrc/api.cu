@@ -130,6 +130,13 @@ int zkb_sync(zkb_ctx* ctx) {
   return ZKB_OK;
 }
 
+int zkb_set_serial(zkb_ctx* ctx, int on) {
+  if (!ctx) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->serial = on != 0;
+  return ZKB_OK;
+}
+
 // ---- kernel timing (bench.py's roofline figure) ------------------------------------------------
 int zkb_prof_enable(zkb_ctx* ctx, int on) {
   if (!ctx) return ZKB_E_INVALID;

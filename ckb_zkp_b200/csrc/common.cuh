@@ -40,6 +40,7 @@ struct zkb_ctx {
   std::mutex mu;
   std::string err;
   uint64_t launches = 0;
+  bool serial = false;      // zkb_set_serial: the prove path uses one stream (measurement aid)
   int sm_count = zkb::kSMs;
   std::map<int, zkb::NttDomain*> domains;   // key = curve * 64 + log_n
   zkb::Groth16Stage* stage = nullptr;

@@ -303,6 +303,9 @@ struct Groth16Impl {
     if (!pk || pk->curve != CURVE || pk->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "groth16: bad proving key");
     if (!r || !sc) return set_err(ctx, ZKB_E_INVALID, "groth16: null r/s");
     cudaStream_t st = ctx->main;
+    // serial mode (zkb_set_serial): every kernel on the main stream, for per-kernel timing without overlap
+    cudaStream_t side[kNumSideStreams];
+    for (int i = 0; i < kNumSideStreams; i++) side[i] = ctx->serial ? st : ctx->side[i];
     const GroupOps* g1 = group_ops(CURVE, ZKB_G1);
     const GroupOps* g2 = group_ops(CURVE, ZKB_G2);
     Res* res = (Res*)s->results;
@@ -314,7 +317,7 @@ struct Groth16Impl {
     memcpy(s_val.v, sc, 32);
     // the four delta multiples are independent of everything else: side stream, joined before the assembly
     ZKB_TRY(fork_streams(ctx, 1));
-    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, ctx->side[0], r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
+    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, side[0], r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
                (const Affine<Fq2>*)pk->g2_singles, res);
     // assignment = into_repr(input[1..] ++ aux)  (prover.rs:150-158)
     const size_t n_assign = s->n_inputs - 1 + s->n_aux;
@@ -328,18 +331,18 @@ struct Groth16Impl {
     // (s * g_a, r * g1_b) hang off them: they run on side[5] under the H and L accumulations, so that
     // after the last bucket reduction only the five additions and the inversion of proof.c remain.
     ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-    for (int i = 1; i <= 5; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
-    ZKB_TRY(g2->msm_run(ctx, ctx->side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
-    ZKB_TRY(g1->msm_run(ctx, ctx->side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
-    ZKB_TRY(g1->msm_run(ctx, ctx->side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
+    for (int i = 1; i <= 5; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(side[i], ctx->ev_fork, 0));
+    ZKB_TRY(g2->msm_run(ctx, side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
+    ZKB_TRY(g1->msm_run(ctx, side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
+    ZKB_TRY(g1->msm_run(ctx, side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
     for (int i : {0, 1, 2, 4}) {
-      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
-      ZKB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[5], ctx->ev_join[i], 0));
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
+      ZKB_CUDA(ctx, cudaStreamWaitEvent(side[5], ctx->ev_join[i], 0));
     }
-    ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, ctx->side[5], (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
+    ZKB_LAUNCH(ctx, (k_g16_coeffs<FrP, Fq, Fq2>), 3, 32, 0, side[5], (const Fr*)scal, (const Affine<Fq>*)pk->a->table,
                (const Affine<Fq>*)pk->b_g1->table, (const Affine<Fq2>*)pk->b_g2->table,
                (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles, res);
-    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 2, 32, 0, ctx->side[5], res, 0u);
+    ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 2, 32, 0, side[5], res, 0u);
     if (s->pending[0]) {
       ZKB_TRY(upload_csr(ctx, st, &s->A, s->pending[0]));
       ZKB_TRY(upload_csr(ctx, st, &s->B, s->pending[1]));
@@ -348,9 +351,9 @@ struct Groth16Impl {
     }
     ZKB_TRY(compute_h(ctx, st));
     ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
-    ZKB_TRY(g1->msm_run(ctx, ctx->side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    ZKB_TRY(g1->msm_run(ctx, side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
     for (int i : {3, 5}) {
-      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
       ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
     }
     ZKB_LAUNCH(ctx, (k_g16_finish<Fq, Fq2>), 1, 32, 0, st, res, 2u);

@@ -493,9 +493,11 @@ inline int msm_pair_levels(size_t max_entries, uint32_t n_buckets) {
   return 0;
 }
 
-inline int pair_level_occupancy(const void* kernel) {
+inline int pair_level_occupancy(const void* kernel, size_t smem_bytes) {
   int blocks = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kPairThreads, 0) != cudaSuccess || blocks < 1) blocks = 1;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kPairThreads, smem_bytes) != cudaSuccess || blocks < 1)
+    blocks = 1;
   return blocks;
 }
 
@@ -572,12 +574,13 @@ struct MsmEngine {
     if (levels > 0) {
       auto halved = [&](size_t e) { return (e + (e < n_buckets ? e : (size_t)n_buckets) + 1) / 2; };
       const size_t e1 = halved(max_entries), e2 = halved(e1);
-      uint32_t *off_a, *off_b, *meta;
+      uint32_t *off_a, *off_b;
+      uint2* recs;
       F* prefix;
       Aff *pts_a, *pts_b;
       ZKB_TRY(ws.alloc(&off_a, (size_t)n_buckets + 1));
       ZKB_TRY(ws.alloc(&off_b, (size_t)n_buckets + 1));
-      ZKB_TRY(ws.alloc(&meta, e1));
+      ZKB_TRY(ws.alloc(&recs, e1));
       ZKB_TRY(ws.alloc(&prefix, e1));
       ZKB_TRY(ws.alloc(&pts_a, e1));
       ZKB_TRY(ws.alloc(&pts_b, levels > 1 ? e2 : 1));
@@ -592,26 +595,12 @@ struct MsmEngine {
         ZKB_LAUNCH(ctx, k_scan_finish, ceil_div(n_buckets, 256), 256, 0, st, off_out, n_buckets, tile_sums, n_tiles,
                    (uint32_t*)nullptr);
         // one resident wave; the kernel derives the slots per thread from the list length on the device
-        {
-          static bool pf_set = false;
-          if (!pf_set) {
-            pf_set = true;
-            if (const char* e = getenv("ZKB_PAIR_PF")) { int v = atoi(e); cudaMemcpyToSymbol(g_pair_prefetch, &v, sizeof v); }
-          }
-        }
         ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
+          static const int occ = pair_level_occupancy((const void*)k_pair_level<F>, PairRing<F>::kBytes);
           prof_begin(ctx, bs);
-          if (lvl == 0) {
-            static const int occ = pair_level_occupancy((const void*)k_pair_level<F, true>);
-            ZKB_LAUNCH(ctx, (k_pair_level<F, true>), (unsigned)(ctx->sm_count * occ), kPairThreads, 0, bs,
-                       (PairSrc<F, true>{entries, (const Aff*)srs->table}), off_in, (const uint32_t*)off_out, n_buckets, meta,
-                       prefix, pts_out);
-          } else {
-            static const int occ = pair_level_occupancy((const void*)k_pair_level<F, false>);
-            ZKB_LAUNCH(ctx, (k_pair_level<F, false>), (unsigned)(ctx->sm_count * occ), kPairThreads, 0, bs,
-                       (PairSrc<F, false>{nullptr, acc_pts}), off_in, (const uint32_t*)off_out, n_buckets, meta, prefix,
-                       pts_out);
-          }
+          ZKB_LAUNCH(ctx, (k_pair_level<F>), (unsigned)(ctx->sm_count * occ), kPairThreads, PairRing<F>::kBytes, bs,
+                     lvl == 0 ? (const uint32_t*)entries : (const uint32_t*)nullptr, lvl == 0 ? (const Aff*)srs->table : acc_pts,
+                     off_in, (const uint32_t*)off_out, n_buckets, recs, prefix, pts_out);
           prof_end(ctx, bs, 0.0);
           return ZKB_OK;
         }));

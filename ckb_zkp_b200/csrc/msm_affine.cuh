@@ -4,8 +4,8 @@
 // of a bucket by ceil(k / 2) points, adding neighbours (2j, 2j + 1) in affine coordinates and
 // carrying an odd leftover over.  All additions of a level are independent, so their
 // denominators (x1 - x0, or 2y for a doubling) share inversions by Montgomery's trick: a thread
-// owns M consecutive output slots and multiplies its M denominators into a running product (stored
-// per slot); the 128 products of a block are multiplied up a tree in shared memory, the root is
+// owns M output slots and multiplies its M denominators into a running product (stored per
+// slot); the 128 products of a block are multiplied up a tree in shared memory, the root is
 // inverted ONCE with the shift-and-subtract Euclid of field.cuh (add / logic pipe: it overlaps the
 // multiplier work of the other resident blocks), the inverses travel back down the tree, and each
 // thread walks back through its slots finishing every addition with 1/d = running inverse * prefix.
@@ -13,6 +13,14 @@
 // 8 + 2 of the XYZZ mixed addition, and no bucket is "big": a bucket with a million entries is
 // half a million independent pairs.  After the levels the (much shorter) lists go through the
 // XYZZ accumulation of msm.cuh unchanged.
+//
+// Memory schedule of one level (what keeps the multiplier fed): a block owns a contiguous range of
+// 128 * M slots per pass.  Phase 0 resolves every slot to its two source indices (8-byte record;
+// contiguous slots per thread, so the bucket walk is cheap).  The forward and backward phases then
+// visit the range TRANSPOSED -- iteration i of thread t is slot base + 128 i + t -- so records,
+// prefix products and results stream through HBM coalesced, and the operands of the next slot(s)
+// are copied into a per-thread shared-memory ring with cp.async while the current slot multiplies
+// (no registers held, no scoreboard stall: the gathers of level 0 are ~1 us away).
 //
 // A level is: k_pair_sizes -> exclusive scan (msm.cuh) -> k_pair_level.
 // Identity = affine (0, 0), as everywhere on the device; P + (-P), doublings and identities are
@@ -27,7 +35,7 @@ namespace zkb {
 constexpr int kPairThreads = 128;             // threads per block = leaves of the shared inversion tree
 constexpr uint32_t kPairMinM = 4;             // output slots per thread and pass: lower / upper limit
 constexpr uint32_t kPairMaxM = 128;
-constexpr uint32_t kPairFlag = 0x80000000u;   // meta: the slot adds two points (else it copies one)
+constexpr uint32_t kPairNone = 0xffffffffu;   // second source of a slot that only carries one point over
 
 // cnt_out[b] = ceil(k_b / 2)
 static __global__ void k_pair_sizes(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ cnt_out) {
@@ -35,76 +43,41 @@ static __global__ void k_pair_sizes(const uint32_t* __restrict__ off_in, uint32_
   if (b < nb) cnt_out[b] = (off_in[b + 1] - off_in[b] + 1) >> 1;
 }
 
-// pull [p, p + bytes) towards L1 (no destination register: the data is loaded normally one iteration later)
-static __device__ int g_pair_prefetch = 0;             // 0 none, 1 L1, 2 L2 (tuning switch, set from ZKB_PAIR_PF)
-__device__ __forceinline__ void prefetch_l1(const void* p, uint32_t bytes) {
-  const char* c = (const char*)p;
-  const int mode = g_pair_prefetch;
-  if (mode == 1) {
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(c));
-    if ((((uintptr_t)c) & 127u) + bytes > 128u) asm volatile("prefetch.global.L1 [%0];" ::"l"(c + bytes - 1));
-  } else if (mode == 2) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(c));
-    if ((((uintptr_t)c) & 127u) + bytes > 128u) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 1));
-  }
+// ---- cp.async (16-byte, L2 only) -----------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// where the points of a level come from: level 0 gathers them from the base table through the sorted
-// (negate | index) entries, later levels read the previous level's dense output
-template <class F, bool GATHER>
-struct PairSrc {
-  const uint32_t* entries;
-  const Affine<F>* pts;
-  __device__ __forceinline__ const Affine<F>* at(uint32_t pos, bool& neg) const {
-    if (GATHER) {
-      uint32_t e = __ldg(entries + pos);
-      neg = (e >> 31) != 0;
-      return pts + (e & 0x7fffffffu);
-    }
-    neg = false;
-    return pts + pos;
-  }
-  __device__ __forceinline__ F coord(const F* p) const { return GATHER ? ld_vec(p) : ld_vec_rw(p); }
-  __device__ __forceinline__ Affine<F> point(uint32_t pos) const {
-    bool neg;
-    const Affine<F>* a = at(pos, neg);
-    Affine<F> p = GATHER ? ld_vec(a) : ld_vec_rw(a);
-    if (neg) p.y = F::neg(p.y);
-    return p;
-  }
-  __device__ __forceinline__ void prefetch_x(uint32_t pos) const {
-    bool neg;
-    prefetch_l1(&at(pos, neg)->x, sizeof(F));
-  }
-  __device__ __forceinline__ void prefetch(uint32_t pos) const {
-    bool neg;
-    prefetch_l1(at(pos, neg), sizeof(Affine<F>));
-  }
-  // x coordinates of points[pos], points[pos + 1] (what the denominator needs in the common case)
-  __device__ __forceinline__ void fetch_x(uint32_t pos, F& x0, F& x1) const {
-    bool n0, n1;
-    x0 = coord(&at(pos, n0)->x);
-    x1 = coord(&at(pos + 1, n1)->x);
-  }
-  // denominator of points[pos] + points[pos + 1] given their x; false when the sum needs no inversion
-  // (an identity operand, or P + (-P)).  The y coordinates are only read on the rare paths.
-  __device__ __forceinline__ bool denominator(uint32_t pos, const F& x0, const F& x1, F& d) const {
-    bool n0, n1;
-    if (x0.is_zero() && coord(&at(pos, n0)->y).is_zero()) return false;
-    if (x1.is_zero() && coord(&at(pos + 1, n1)->y).is_zero()) return false;
-    d = F::sub(x1, x0);
-    if (!d.is_zero()) return true;
-    F y0 = coord(&at(pos, n0)->y), y1 = coord(&at(pos + 1, n1)->y);
-    if (n0) y0 = F::neg(y0);
-    if (n1) y1 = F::neg(y1);
-    if (y0 == y1 && !y0.is_zero()) { d = F::dbl(y0); return true; }
-    return false;
+// Per-thread operand ring in shared memory: 16-byte chunk c of stage s of thread t sits at
+// ((s * CH + c) * 128 + t) * 16, so a warp's 128-bit accesses are conflict free.
+template <class F>
+struct PairRing {
+  static constexpr int CHX = sizeof(F) / 16;            // chunks of one coordinate
+  static constexpr int CHP = 2 * CHX;                   // chunks of one point
+  static constexpr int CH_FULL = 2 * CHP;               // backward stage: two points
+  static constexpr int CH_X = 2 * CHX;                  // forward stage: two x coordinates
+  static constexpr int STAGES_FULL = 2;
+  static constexpr int STAGES_X = 4;                    // same bytes: 4 * CH_X == 2 * CH_FULL
+  static constexpr int kChunks = STAGES_FULL * CH_FULL;
+  static constexpr size_t kBytes = (size_t)kChunks * kPairThreads * 16;      // >= 2 * kPairThreads * sizeof(F) (the tree)
+  uint4* base;                                          // block's ring + threadIdx.x
+  __device__ __forceinline__ uint4* chunk(int idx) const { return base + idx * kPairThreads; }
+  __device__ __forceinline__ F load(int first_chunk) const {
+    F r;
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int c = 0; c < CHX; c++) d[c] = *chunk(first_chunk + c);
+    return r;
   }
 };
 
 // r = p + q in affine coordinates, 1/d taken from the shared inversion chain (see k_pair_level)
 template <class F>
-__device__ __forceinline__ void pair_finish(Affine<F>& r, const Affine<F>& q, F& inv_run, const F* prefix_prev, bool chain_more) {
+__device__ __forceinline__ void pair_finish(Affine<F>& r, const Affine<F>& q, F& inv_run, const F& prefix_prev, bool chain_more) {
   if (r.is_inf()) { r = q; return; }
   if (q.is_inf()) return;
   F d = F::sub(q.x, r.x), num;
@@ -122,7 +95,7 @@ __device__ __forceinline__ void pair_finish(Affine<F>& r, const Affine<F>& q, F&
   }
   F inv_d = inv_run;
   if (chain_more) {
-    inv_d = F::mul(inv_run, *prefix_prev);
+    inv_d = F::mul(inv_run, prefix_prev);
     inv_run = F::mul(inv_run, d);
   }
   F lam = F::mul(num, inv_d);
@@ -131,17 +104,41 @@ __device__ __forceinline__ void pair_finish(Affine<F>& r, const Affine<F>& q, F&
   r.x = x3;
 }
 
-// One level.  off_in / off_out: bucket offsets of the input / output lists (nb + 1 each).  The grid is
-// sized to one resident wave; every thread takes M = ceil(E / threads) consecutive output slots (E is only
-// known on the device), in several passes when that exceeds kPairMaxM.  Per pass and block: forward
-// products per thread -> product tree over the block's 128 threads in shared memory -> ONE inversion
-// (thread 0) -> inverses pushed back down the tree -> backward pass finishing the additions.
-template <class F, bool GATHER>
+// denominator of P0 + P1 given their x; false when the sum needs no inversion (an identity operand, or
+// P + (-P)).  The y coordinates are only read (from global memory) on the rare paths.
+template <class F>
+__device__ __forceinline__ bool pair_denominator(const Affine<F>* pts, uint2 rec, const F& x0, const F& x1, F& d) {
+  const Affine<F>* a0 = pts + (rec.x & 0x7fffffffu);
+  const Affine<F>* a1 = pts + (rec.y & 0x7fffffffu);
+  if (x0.is_zero() && ld_vec_rw(&a0->y).is_zero()) return false;
+  if (x1.is_zero() && ld_vec_rw(&a1->y).is_zero()) return false;
+  d = F::sub(x1, x0);
+  if (!d.is_zero()) return true;
+  F y0 = ld_vec_rw(&a0->y), y1 = ld_vec_rw(&a1->y);
+  if (rec.x >> 31) y0 = F::neg(y0);
+  if (rec.y >> 31) y1 = F::neg(y1);
+  if (y0 == y1 && !y0.is_zero()) { d = F::dbl(y0); return true; }
+  return false;
+}
+
+// One level.  entries != nullptr (level 0): the input lists are the sorted (negate | table index) entries and
+// pts is the base table; else the lists are the previous level's dense points.  off_in / off_out: bucket
+// offsets of the input / output lists (nb + 1 each).  The grid is one resident wave; a block takes
+// 128 * M slots per pass with M = ceil(E / threads) derived on the device (E is only known there), in
+// several equal passes when that exceeds kPairMaxM.
+template <class F>
 __global__ void __launch_bounds__(kPairThreads, sizeof(F) <= 48 ? 3 : 2)
-k_pair_level(PairSrc<F, GATHER> src, const uint32_t* __restrict__ off_in, const uint32_t* __restrict__ off_out,
-             uint32_t nb, uint32_t* __restrict__ meta, F* __restrict__ prefix, Affine<F>* __restrict__ out) {
-  __shared__ F tree[2 * kPairThreads];            // node i: children 2i, 2i + 1; leaves at kPairThreads + tid
+k_pair_level(const uint32_t* __restrict__ entries, const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ off_in,
+             const uint32_t* __restrict__ off_out, uint32_t nb, uint2* __restrict__ recs, F* __restrict__ prefix,
+             Affine<F>* __restrict__ out) {
+  using Ring = PairRing<F>;
+  // dynamic shared memory (PairRing<F>::kBytes): the operand ring; between the forward and the backward phase,
+  // while the ring is idle, its first bytes hold the inversion tree (node i: children 2i, 2i + 1; leaves at
+  // kPairThreads + tid)
+  extern __shared__ uint4 pair_smem[];
+  F* tree = reinterpret_cast<F*>(pair_smem);
   const uint32_t tid = threadIdx.x;
+  Ring ring{pair_smem + tid};
   const uint32_t E = off_out[nb];
   const uint32_t T = gridDim.x * kPairThreads;
   uint32_t M = (E + T - 1) / T;
@@ -151,50 +148,81 @@ k_pair_level(PairSrc<F, GATHER> src, const uint32_t* __restrict__ off_in, const 
   }
   if (M < kPairMinM) M = kPairMinM;
   const uint64_t per_pass = (uint64_t)T * M;
-  for (uint64_t base = (uint64_t)blockIdx.x * kPairThreads * M; base < E; base += per_pass) {   // block-uniform
-    const uint64_t first = base + (uint64_t)tid * M;
-    const uint32_t o0 = (uint32_t)(first < E ? first : E);
-    const uint32_t cnt = E - o0 < M ? E - o0 : M;
+  for (uint64_t base64 = (uint64_t)blockIdx.x * kPairThreads * M; base64 < E; base64 += per_pass) {   // block-uniform
+    const uint32_t base = (uint32_t)base64;
+    const uint32_t range_end = E - base < kPairThreads * M ? E : base + kPairThreads * M;
 
-    // ---- forward: slot -> source position, running product of the denominators
+    // ---- phase 0: slot -> (source 0, source 1) records; thread t resolves slots [base + t M, base + (t + 1) M)
+    {
+      const uint32_t o0 = base + tid * M < range_end ? base + tid * M : range_end;
+      const uint32_t o1 = o0 + M < range_end ? o0 + M : range_end;
+      if (o0 < o1) {
+        uint32_t lo = 0, hi = nb;                 // off_out[lo] <= o0 < off_out[hi]
+        while (hi - lo > 1) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (off_out[mid] <= o0) lo = mid; else hi = mid;
+        }
+        uint32_t b = lo, b_beg = off_out[b], b_end = off_out[b + 1], in_beg = off_in[b], in_end = off_in[b + 1];
+        for (uint32_t o = o0; o < o1; o++) {
+          while (o >= b_end) {                    // next non-empty bucket
+            b++;
+            b_beg = b_end;
+            b_end = off_out[b + 1];
+            in_beg = off_in[b];
+            in_end = off_in[b + 1];
+          }
+          const uint32_t s0 = in_beg + 2 * (o - b_beg);
+          uint2 rec;
+          rec.x = entries ? __ldg(entries + s0) : s0;
+          rec.y = s0 + 1 < in_end ? (entries ? __ldg(entries + s0 + 1) : s0 + 1) : kPairNone;
+          recs[o] = rec;
+        }
+      }
+    }
+    __syncthreads();                              // records are read back transposed below
+
+    // slots of this thread: o(i) = base + tid + 128 i, i < cnt
+    const uint32_t cnt = base + tid < range_end ? (range_end - base - tid + kPairThreads - 1) / kPairThreads : 0;
+    auto slot = [&](uint32_t i) { return base + tid + i * kPairThreads; };
+
+    // ---- forward: running product of the denominators; x coordinates staged STAGES_X - 1 slots ahead
     F run = F::one();
-    if (cnt) {
-      uint32_t lo = 0, hi = nb;                   // off_out[lo] <= o0 < off_out[hi]
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (off_out[mid] <= o0) lo = mid; else hi = mid;
-      }
-      uint32_t b = lo, b_beg = off_out[b], b_end = off_out[b + 1], in_beg = off_in[b], in_end = off_in[b + 1];
-      auto locate = [&](uint32_t o) -> uint32_t {   // meta word of slot o (slots are visited in order)
-        while (o >= b_end) {                      // next non-empty bucket
-          b++;
-          b_beg = b_end;
-          b_end = off_out[b + 1];
-          in_beg = off_in[b];
-          in_end = off_in[b + 1];
+    {
+      auto stage_x = [&](uint32_t i) {            // copy the two x of slot i into ring stage i % STAGES_X
+        if (i < cnt) {
+          const uint2 rec = recs[slot(i)];
+          if (rec.y != kPairNone) {
+            const int s = (int)(i % Ring::STAGES_X) * Ring::CH_X;
+            const uint4* g0 = reinterpret_cast<const uint4*>(&pts[rec.x & 0x7fffffffu].x);
+            const uint4* g1 = reinterpret_cast<const uint4*>(&pts[rec.y & 0x7fffffffu].x);
+#pragma unroll
+            for (int c = 0; c < Ring::CHX; c++) {
+              cp_async16(ring.chunk(s + c), g0 + c);
+              cp_async16(ring.chunk(s + Ring::CHX + c), g1 + c);
+            }
+          }
         }
-        const uint32_t s0 = in_beg + 2 * (o - b_beg);
-        return s0 | (s0 + 1 < in_end ? kPairFlag : 0u);
+        cp_async_commit();                        // one group per slot, empty or not: wait counts stay uniform
       };
-      uint32_t m = locate(o0);
+#pragma unroll
+      for (int k = 0; k < Ring::STAGES_X - 1; k++) stage_x(k);
       for (uint32_t i = 0; i < cnt; i++) {
-        const uint32_t o = o0 + i;
-        uint32_t m_next = 0;
-        if (i + 1 < cnt) {                        // pull the next slot's operands towards L1 while this one multiplies
-          m_next = locate(o + 1);
+        stage_x(i + Ring::STAGES_X - 1);
+        cp_async_wait<Ring::STAGES_X - 1>();      // slot i has landed
+        const uint2 rec = recs[slot(i)];
+        if (rec.y != kPairNone) {
+          const int s = (int)(i % Ring::STAGES_X) * Ring::CH_X;
+          const F x0 = ring.load(s), x1 = ring.load(s + Ring::CHX);
+          F d;
+          if (pair_denominator(pts, rec, x0, x1, d)) run = F::mul(run, d);
         }
-        meta[o] = m;
-        if (m & kPairFlag) {
-          F x0, x1, d;
-          src.fetch_x(m & ~kPairFlag, x0, x1);
-          if (src.denominator(m & ~kPairFlag, x0, x1, d)) run = F::mul(run, d);
-        }
-        st_vec(&prefix[o], run);
-        m = m_next;
+        st_vec(&prefix[slot(i)], run);
       }
+      cp_async_wait<0>();
     }
 
     // ---- one inversion per block: product tree up, inverse, inverses down
+    __syncthreads();                              // all threads are done with the ring: the tree takes its place
     tree[kPairThreads + tid] = run;
     __syncthreads();
     for (uint32_t s = kPairThreads / 2; s >= 1; s >>= 1) {
@@ -213,25 +241,46 @@ k_pair_level(PairSrc<F, GATHER> src, const uint32_t* __restrict__ off_in, const 
       __syncthreads();
     }
     F inv_run = tree[kPairThreads + tid];
+    __syncthreads();                              // every leaf is read before the ring overwrites the tree
 
-    // ---- backward: finish the additions.  The operands of slot i - 1 (two gathered points and the prefix
-    // product) are pulled towards L1 while slot i computes; meta and entries are walked contiguously,
-    // so reading them early to form the addresses costs L1 hits only.
-    if (cnt) {
-      uint32_t i = cnt;
-      while (i-- > 0) {
-        const uint32_t o = o0 + i;
-        const uint32_t m = meta[o];
-        Affine<F> r = src.point(m & ~kPairFlag);
-        if (m & kPairFlag) {
-          Affine<F> q = src.point((m & ~kPairFlag) + 1);
-          F pre = i > 0 ? ld_vec_rw(&prefix[o - 1]) : F::one();
-          pair_finish(r, q, inv_run, &pre, i > 0);
+    // ---- backward: finish the additions; both points of the next slot staged while this one computes
+    {
+      auto stage_full = [&](uint32_t i) {         // i counts down; i >= cnt (wrapped below 0) means nothing left
+        if (i < cnt) {
+          const int s = (int)(i & 1) * Ring::CH_FULL;
+          const uint2 rec = recs[slot(i)];
+          const uint4* g0 = reinterpret_cast<const uint4*>(&pts[rec.x & 0x7fffffffu]);
+#pragma unroll
+          for (int c = 0; c < Ring::CHP; c++) cp_async16(ring.chunk(s + c), g0 + c);
+          if (rec.y != kPairNone) {
+            const uint4* g1 = reinterpret_cast<const uint4*>(&pts[rec.y & 0x7fffffffu]);
+#pragma unroll
+            for (int c = 0; c < Ring::CHP; c++) cp_async16(ring.chunk(s + Ring::CHP + c), g1 + c);
+          }
         }
-        st_vec(&out[o], r);
+        cp_async_commit();
+      };
+      if (cnt) stage_full(cnt - 1);
+      F pre = cnt > 1 ? ld_vec_rw(&prefix[slot(cnt - 2)]) : F::one();
+      for (uint32_t i = cnt; i-- > 0;) {
+        stage_full(i - 1);                        // i == 0 wraps to 0xffffffff >= cnt: empty group
+        const F pre_next = i > 1 ? ld_vec_rw(&prefix[slot(i - 2)]) : F::one();
+        cp_async_wait<1>();                       // slot i has landed
+        const uint2 rec = recs[slot(i)];
+        const int s = (int)(i & 1) * Ring::CH_FULL;
+        Affine<F> r{ring.load(s), ring.load(s + Ring::CHX)};
+        if (rec.x >> 31) r.y = F::neg(r.y);
+        if (rec.y != kPairNone) {
+          Affine<F> q{ring.load(s + Ring::CHP), ring.load(s + Ring::CHP + Ring::CHX)};
+          if (rec.y >> 31) q.y = F::neg(q.y);
+          pair_finish(r, q, inv_run, pre, i > 0);
+        }
+        st_vec(&out[slot(i)], r);
+        pre = pre_next;
       }
+      cp_async_wait<0>();
     }
-    __syncthreads();                              // the tree is reused by the next pass
+    __syncthreads();                              // tree, ring and records are reused by the next pass
   }
 }
 

@@ -76,6 +76,9 @@ uint64_t zkb_launch_count(zkb_ctx* ctx);
 /* CUDA-event timing of the dominant kernel (MSM bucket accumulation) on its launch stream:
  * enable resets the counters; read synchronises and returns the summed duration, the number of
  * launches and the algorithmic bytes (n * (32 + sizeof affine base) per MSM) they covered. */
+/* Measurement aid: with on != 0 the Groth16 prove path enqueues every kernel on ONE stream, so the per-kernel
+ * event timings of zkb_prof_* are kernel durations (no queueing behind concurrent kernels). */
+int zkb_set_serial(zkb_ctx* ctx, int on);
 int zkb_prof_enable(zkb_ctx* ctx, int on);
 int zkb_prof_read(zkb_ctx* ctx, double* ms_total, uint64_t* launches, double* alg_bytes_total);
 
