@@ -38,7 +38,16 @@ ap.add_argument("--no-verify", action="store_true")
 ap.add_argument("--host-buffers", action="store_true", help="round state in host arrays (one H2D/D2H per primitive)")
 a = ap.parse_args()
 
-ctx = Context(0)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+import torch  # noqa: E402
+if world > 1:                              # weak scaling: every rank proves its own instance, no data-path collective
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+torch.cuda.set_device(local)
+ctx = Context(local)
 
 # per-primitive wall-clock accounting (host-buffer API: includes the copies of each call)
 PROF = {}
@@ -58,6 +67,9 @@ for _name in ("msm", "ntt", "fr_vec_op", "fr_batch_inverse", "spmv", "fr_powers"
 
 
 def prof_report(tag, total):
+    if rank:
+        PROF.clear()
+        return
     acc = sum(v[1] for v in PROF.values())
     print("%s: %.3f s total, %.3f s inside backend calls; %s" % (tag, total, acc, ", ".join(
         "%s %dx %.3fs" % (k, v[0], v[1]) for k, v in sorted(PROF.items(), key=lambda kv: -kv[1][1]))), file=sys.stderr, flush=True)
@@ -68,7 +80,7 @@ f = zm.Field(curve)
 p = f.p
 n = (1 << a.log_h) - 4                      # real constraints; n + 3 variables -> 3 empty constraints appended
 t0 = time.perf_counter()
-inst = synth.MimcInstance(curve, n)
+inst = synth.MimcInstance(curve, n, seed=synth.MIMC_SEED + rank)
 A, B, C, z_mont = inst.device_form(ctx)
 ni, nv = inst.n_inputs, inst.n_inputs + inst.n_aux
 index, extra = zm.index(ctx, curve, A, B, C, ni, nv)
@@ -163,6 +175,10 @@ for i in range(a.steps):
     prof_report('prove', times[-1])
 launches = (ctx.launch_count - launches0) // a.steps
 sec = sum(times) / len(times)
+if world > 1:
+    t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t[0])
 
 checked = None
 if not a.no_verify:
@@ -183,7 +199,8 @@ if not a.no_verify:
             xy, inf = ctx.fixed_base_mul(curve, 1, gen, synth.ints_to_limbs([e]))
             checked = checked and bool(inf[0]) == bool(got[1]) and (bool(got[1]) or np.array_equal(xy[0], got[0]))
 
-line = {"metric": "marlin_proofs_per_sec_bn254_2e%d_constraints" % a.log_h, "value": 1.0 / sec, "unit": "proofs/s", "n_gpus": 1,
+line = {"metric": "marlin_proofs_per_sec_bn254_2e%d_constraints" % a.log_h, "value": world / sec, "unit": "proofs/s", "n_gpus": world,
+        "scaling": "weak",
         "steps": a.steps, "ms_per_step": sec * 1e3, "higher_is_better": True, "data": "synthetic",
         "dtype": "u32 limbs (modular integer arithmetic, 254-bit Fr / Fq)",
         "config": {"workload": "Marlin prove, %s, MiMC chain with %d constraints: |H| = 2^%d, |K| = 2^%d, |B| = 2^%d, "
@@ -195,6 +212,10 @@ line = {"metric": "marlin_proofs_per_sec_bn254_2e%d_constraints" % a.log_h, "val
                              % ("in host arrays between primitives" if a.host_buffers else "resident in HBM"),
                    "commitments": len(out[0]), "openings": len(out[2])},
         "gpu_launches": launches, "index_s": round(index_s, 2), "setup_s": round(setup_s, 2), "verified": checked}
-print(json.dumps(line))
+if rank == 0:
+    print(json.dumps(line))
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
 ck.free()
 ctx.close()
