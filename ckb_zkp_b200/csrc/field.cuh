@@ -169,6 +169,132 @@ struct alignas(16) Fp {
   }
   ZKB_HD static Fp sqr(const Fp& a) { return mul(a, a); }
 
+  // ---- alternative: Karatsuba product + separated reduction ---------------------------------------
+  // out[0 .. 2H) = a[0 .. H) * b[0 .. H).  Same even / odd accumulator idea as mul(): the product of
+  // limbs (i, j) lands at position i + j, even positions accumulate in X, odd ones in Y (stored one limb
+  // lower), so every IMAD.WIDE hits an aligned register pair; each row is two carry chains whose carry
+  // out goes to the next limb, which at that point holds at most a carry bit of the previous row.
+  template <int H>
+  ZKB_HD static void wide_mul(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    static_assert(H % 2 == 0, "even half size expected");
+    uint32_t X[2 * H], Y[2 * H];
+#pragma unroll
+    for (int k = 0; k < 2 * H; k++) X[k] = Y[k] = 0;
+#pragma unroll
+    for (int j = 0; j < H; j += 2) ptx::mul_wide(X[j], X[j + 1], a[j], b[0]);
+#pragma unroll
+    for (int j = 1; j < H; j += 2) ptx::mul_wide(Y[j - 1], Y[j], a[j], b[0]);
+#pragma unroll
+    for (int i = 1; i < H; i++) {
+      if (i % 2 == 0) {
+        ptx::mad_wide_cc(X[i], X[i + 1], a[0], b[i]);
+#pragma unroll
+        for (int j = 2; j < H; j += 2) ptx::madc_wide_cc(X[i + j], X[i + j + 1], a[j], b[i]);
+        X[i + H] = ptx::addc(X[i + H], 0);
+        ptx::mad_wide_cc(Y[i], Y[i + 1], a[1], b[i]);
+#pragma unroll
+        for (int j = 3; j < H; j += 2) ptx::madc_wide_cc(Y[i + j - 1], Y[i + j], a[j], b[i]);
+        Y[i + H] = ptx::addc(Y[i + H], 0);
+      } else {
+        ptx::mad_wide_cc(Y[i - 1], Y[i], a[0], b[i]);
+#pragma unroll
+        for (int j = 2; j < H; j += 2) ptx::madc_wide_cc(Y[i + j - 1], Y[i + j], a[j], b[i]);
+        Y[i + H - 1] = ptx::addc(Y[i + H - 1], 0);
+        ptx::mad_wide_cc(X[i + 1], X[i + 2], a[1], b[i]);
+#pragma unroll
+        for (int j = 3; j < H; j += 2) ptx::madc_wide_cc(X[i + j], X[i + j + 1], a[j], b[i]);
+        if (i + H + 1 < 2 * H) X[i + H + 1] = ptx::addc(X[i + H + 1], 0);     // top row: X < 2^(64 H), no carry out
+      }
+    }
+    out[0] = X[0];
+    out[1] = ptx::add_cc(X[1], Y[0]);
+#pragma unroll
+    for (int k = 2; k < 2 * H - 1; k++) out[k] = ptx::addc_cc(X[k], Y[k - 1]);
+    out[2 * H - 1] = ptx::addc(X[2 * H - 1], Y[2 * H - 2]);
+  }
+  // T[0 .. 2N) = a * b with one Karatsuba level: 3 half-size products instead of 4
+  ZKB_HD static void wide_mul_karatsuba(const uint32_t* a, const uint32_t* b, uint32_t* T) {
+    constexpr int H = N / 2;
+    uint32_t sa[H], sb[H], Pm[N + 1];
+    sa[0] = ptx::add_cc(a[0], a[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) sa[k] = ptx::addc_cc(a[k], a[H + k]);
+    const uint32_t ca = ptx::addc(0, 0);
+    sb[0] = ptx::add_cc(b[0], b[H]);
+#pragma unroll
+    for (int k = 1; k < H; k++) sb[k] = ptx::addc_cc(b[k], b[H + k]);
+    const uint32_t cb = ptx::addc(0, 0);
+    wide_mul<H>(a, b, T);
+    wide_mul<H>(a + H, b + H, T + N);
+    wide_mul<H>(sa, sb, Pm);
+    // (sa + ca 2^(32H)) (sb + cb 2^(32H)) = sa sb + 2^(32H) (ca sb + cb sa) + 2^(64H) ca cb
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    Pm[H] = ptx::add_cc(Pm[H], sb[0] & ma);
+#pragma unroll
+    for (int k = 1; k < H; k++) Pm[H + k] = ptx::addc_cc(Pm[H + k], sb[k] & ma);
+    Pm[N] = ptx::addc(0, 0);
+    Pm[H] = ptx::add_cc(Pm[H], sa[0] & mb);
+#pragma unroll
+    for (int k = 1; k < H; k++) Pm[H + k] = ptx::addc_cc(Pm[H + k], sa[k] & mb);
+    Pm[N] = ptx::addc(Pm[N], ca & cb);
+    // middle term = Pm - low product - high product
+    Pm[0] = ptx::sub_cc(Pm[0], T[0]);
+#pragma unroll
+    for (int k = 1; k < N; k++) Pm[k] = ptx::subc_cc(Pm[k], T[k]);
+    Pm[N] = ptx::subc(Pm[N], 0);
+    Pm[0] = ptx::sub_cc(Pm[0], T[N]);
+#pragma unroll
+    for (int k = 1; k < N; k++) Pm[k] = ptx::subc_cc(Pm[k], T[N + k]);
+    Pm[N] = ptx::subc(Pm[N], 0);
+    T[H] = ptx::add_cc(T[H], Pm[0]);
+#pragma unroll
+    for (int k = 1; k <= N; k++) T[H + k] = ptx::addc_cc(T[H + k], Pm[k]);
+#pragma unroll
+    for (int k = H + N + 1; k < 2 * N - 1; k++) T[k] = ptx::addc_cc(T[k], 0);
+    T[2 * N - 1] = ptx::addc(T[2 * N - 1], 0);
+  }
+  // Montgomery reduction of a 2N-limb value T < p R: N rows of the m * p step of mul() on the low half
+  // (the high half does not influence any m), then + high half, then one conditional subtraction.
+  ZKB_HD static void redc_row(uint32_t* X, uint32_t* Y, bool first) {
+    if (!first) {
+      X[0] = ptx::add_cc(X[0], Y[1]);                 // straggler of the previous row
+#pragma unroll
+      for (int k = 0; k < N - 2; k++) Y[k] = ptx::addc_cc(Y[k + 2], 0);     // Y >>= 64, carrying the straggler's carry
+      Y[N - 2] = ptx::addc(0, 0);
+      Y[N - 1] = 0;
+    }
+    uint32_t m = ptx::mul_lo(X[0], P::INV);
+    odd_chain(Y, ModAcc{}, m);
+    even_chain(X, ModAcc{}, m);
+    Y[N - 1] = ptx::addc(Y[N - 1], 0);
+  }
+  ZKB_HD static Fp redc_wide(const uint32_t* T) {
+    uint32_t even[N], odd[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { even[k] = T[k]; odd[k] = 0; }
+#pragma unroll
+    for (int i = 0; i < N; i += 2) {
+      redc_row(even, odd, i == 0);
+      redc_row(odd, even, false);
+    }
+    // (T_low + sum m_k p 2^(32k)) / R = even + (odd >> 32)   (<= p), then the high half (< p^2 / R)
+    uint32_t V[N];
+    V[0] = ptx::add_cc(even[0], odd[1]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) V[k] = ptx::addc_cc(even[k], odd[k + 1]);
+    V[N - 1] = ptx::addc(even[N - 1], 0);
+    V[0] = ptx::add_cc(V[0], T[N]);
+#pragma unroll
+    for (int k = 1; k < N - 1; k++) V[k] = ptx::addc_cc(V[k], T[N + k]);
+    V[N - 1] = ptx::addc(V[N - 1], T[2 * N - 1]);
+    return final_sub(V);
+  }
+  ZKB_HD static Fp mul_sos(const Fp& a, const Fp& b) {
+    uint32_t T[2 * N];
+    wide_mul_karatsuba(a.v, b.v, T);
+    return redc_wide(T);
+  }
+
   ZKB_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }
   ZKB_HD static Fp from_mont(const Fp& a) {
     Fp o = zero();

@@ -264,21 +264,42 @@ k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ 
   uint32_t b = order[t];
   uint32_t pos = offsets[b], end = offsets[b + 1];
   XYZZ<F> acc = XYZZ<F>::inf();
-  uint32_t e = DIRECT ? pos : entries[pos];
-  Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
-  for (;;) {
-    pos++;
-    uint32_t e_next = 0;
-    Affine<F> p_next;
-    bool more = pos < end;
-    if (more) {                                   // fetch the next base while this one is added
-      e_next = DIRECT ? pos : entries[pos];
-      p_next = ld_vec(&table[e_next & 0x7fffffffu]);
+  // G1: the next base travels in registers while this one is added.  G2 points are 48 registers and the XYZZ
+  // accumulator 96, so there the look-ahead is a prefetch instruction (L2) and the load happens in place.
+  constexpr bool kRegPrefetch = sizeof(F) <= 48;
+  if (kRegPrefetch) {
+    uint32_t e = DIRECT ? pos : entries[pos];
+    Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
+    for (;;) {
+      pos++;
+      uint32_t e_next = 0;
+      Affine<F> p_next;
+      bool more = pos < end;
+      if (more) {                                   // fetch the next base while this one is added
+        e_next = DIRECT ? pos : entries[pos];
+        p_next = ld_vec(&table[e_next & 0x7fffffffu]);
+      }
+      if (!DIRECT || !p.is_inf()) acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+      if (!more) break;
+      e = e_next;
+      p = p_next;
     }
-    if (!DIRECT || !p.is_inf()) acc.madd_xy(p.x, p.y, (e >> 31) != 0);
-    if (!more) break;
-    e = e_next;
-    p = p_next;
+  } else {
+    uint32_t e = DIRECT ? pos : entries[pos];
+    for (;;) {
+      pos++;
+      const bool more = pos < end;
+      const uint32_t e_next = more ? (DIRECT ? pos : entries[pos]) : 0;
+      if (more) {
+        const char* nx = reinterpret_cast<const char*>(&table[e_next & 0x7fffffffu]);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + sizeof(Affine<F>) - 1));
+      }
+      const Affine<F> p = ld_vec(&table[e & 0x7fffffffu]);
+      if (!DIRECT || !p.is_inf()) acc.madd_xy(p.x, p.y, (e >> 31) != 0);
+      if (!more) break;
+      e = e_next;
+    }
   }
   st_vec(&bucket_acc[b], acc);
 }

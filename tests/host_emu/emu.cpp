@@ -20,6 +20,7 @@ template <class F> static void fp_op(int op, const uint32_t* a, const uint32_t* 
     case 5: r = F::from_mont(x); break;
     case 6: r = F::sqr(x); break;
     case 7: r = F::neg(x); break;
+    case 8: r = F::mul_sos(x, y); break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));

@@ -155,3 +155,22 @@ def test_point_ops(lib, cid, group):
     K = emu.to_u32(k, 8)
     lib.emu_pt_op(cid, group, 4, emu.ptr(a1), emu.ptr(K), 0, emu.ptr(o))
     assert affine_of(o) == cv.mul_affine(pts[4], k)
+
+
+@pytest.mark.parametrize("fid", [0, 1, 2, 3])
+def test_field_mul_karatsuba_sos(lib, fid):
+    """Fp::mul_sos (one Karatsuba level + separated Montgomery reduction) == a b R^-1 mod p, on edge values that
+    maximise the half sums' carries (all-ones halves) and on random operands."""
+    fp, n = FIELDS[fid]
+    p = fp.p
+    Rinv = pow((1 << (32 * n)) % p, -1, p)
+    rng = random.Random(100 + fid)
+    half = 16 * n
+    vals = edge_values(p) + [((1 << half) - 1), (((1 << half) - 1) << half) % p, p - (1 << half), (1 << (32 * n - 1)) % p]
+    vals += [rng.randrange(p) for _ in range(300)]
+    out = np.zeros(n, dtype=np.uint32)
+    for i, a in enumerate(vals):
+        for b in (vals[(i * 5 + 1) % len(vals)], a, p - 1):
+            A, B = emu.to_u32(a % p, n), emu.to_u32(b % p, n)
+            lib.emu_fp_op(fid, 8, emu.ptr(A), emu.ptr(B), emu.ptr(out))
+            assert emu.from_u32(out) == (a % p) * (b % p) * Rinv % p, (hex(a), hex(b))
