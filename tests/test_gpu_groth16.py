@@ -182,3 +182,23 @@ def test_full_size_witness_map_and_proof(ctx):
     for got, want in zip(proof, ref):
         assert got[1] == want[1] and np.array_equal(got[0], want[0])
     params.free()
+
+
+@pytest.mark.parametrize("name", ["groth16_mimc_bls12_381_2e6", "groth16_mimc_bn254_2e10"])
+def test_serial_measurement_mode_is_the_same_proof(ctx, name):
+    """zkb_set_serial (bench.py's kernel-timing pass: every kernel of the proof on one stream) changes the
+    schedule only: the proof is still the golden one, before, during and after the mode."""
+    g = load(name)
+    params = params_from_golden(ctx, g)
+    A, B, C = matrices(g)
+    args = (params.pk, A, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]), g["r"][0], g["s"][0])
+    assert_proof(g, ctx.groth16_prove(*args))
+    ctx.set_serial(True)
+    try:
+        assert_proof(g, ctx.groth16_prove(*args))
+        ctx.groth16_stage(*args[:7])
+        ctx.groth16_prove_staged(params.pk, g["r"][0], g["s"][0])
+        assert_proof(g, ctx.groth16_fetch_proof(params.pk))
+    finally:
+        ctx.set_serial(False)
+    assert_proof(g, ctx.groth16_prove(*args))
