@@ -96,6 +96,37 @@ __global__ void k_digits(const uint32_t* __restrict__ scalars, uint32_t n, const
   }
 }
 
+// Tiny MSMs over a precomputed table (Marlin's hiding commitments are 2-point MSMs over a 1.5 M-point key): one
+// thread per (pair, window) multiplies the window's table point by its signed digit (<= c bits of double-and-add);
+// the n * W terms are then summed by k_sum_points.  No bucket array, no sort, no reduction passes.
+constexpr uint32_t kSmallMsmTerms = 512;
+template <class F, class FrField>
+__global__ void __launch_bounds__(128)
+k_small_msm_terms(const uint32_t* __restrict__ scalars, uint32_t n, const uint8_t* __restrict__ inf, MsmGeom g,
+                  uint32_t base_offset, int scalars_mont, const Affine<F>* __restrict__ table, XYZZ<F>* __restrict__ terms) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * (uint32_t)g.W) return;
+  const uint32_t i = t / (uint32_t)g.W, j = t % (uint32_t)g.W;
+  XYZZ<F> r = XYZZ<F>::inf();
+  if (!inf[base_offset + i]) {
+    FrField sc = ld_vec(reinterpret_cast<const FrField*>(scalars) + i);
+    if (scalars_mont) sc = FrField::from_mont(sc);
+    const uint32_t half = 1u << (g.c - 1);
+    uint32_t carry = 0, mag = 0, neg = 0;
+    for (uint32_t w = 0; w <= j; w++) {                 // signed digits up to window j (same recoding as k_digits)
+      uint32_t raw = window_bits(sc.v, (int)w * g.c, g.c) + carry;
+      if (raw > half) { mag = (1u << g.c) - raw; neg = 1; carry = 1; }
+      else { mag = raw; neg = 0; carry = 0; }
+    }
+    if (mag) {
+      Affine<F> p = ld_vec(&table[(size_t)j * g.n_srs + base_offset + i]);
+      if (neg) p.y = F::neg(p.y);
+      r = XYZZ<F>::mul_u32(XYZZ<F>::from_affine(p), mag);
+    }
+  }
+  st_vec(&terms[t], r);
+}
+
 // ------------------------------------------------------------------------------------------
 // exclusive scan of the histogram (3 small kernels; <= 2^23 counters)
 // ------------------------------------------------------------------------------------------
@@ -564,6 +595,27 @@ struct MsmEngine {
     MsmGeom g;
     g.c = srs->c; g.W = srs->W; g.B = 1u << (g.c - 1); g.precomp = srs->precomp;
     g.n_srs = (uint32_t)srs->n; g.n_sets = g.precomp ? 1u : (uint32_t)g.W;
+    if (g.precomp && n * (size_t)g.W <= kSmallMsmTerms) {
+      Scratch ws(ctx, st);
+      const uint32_t n_terms = (uint32_t)n * (uint32_t)g.W;
+      Pt *terms, *tmp;
+      ZKB_TRY(ws.alloc(&terms, n_terms));
+      ZKB_TRY(ws.alloc(&tmp, ceil_div(n_terms, 64) + 1));
+      ZKB_LAUNCH(ctx, (k_small_msm_terms<F, Fr>), ceil_div(n_terms, 128), 128, 0, st, d_scalars, (uint32_t)n, srs->inf, g,
+                 (uint32_t)base_offset, scalars_mont, (const Aff*)srs->table, terms);
+      uint32_t n_per = n_terms;
+      Pt *pin = terms, *pout = tmp;
+      while (n_per > 1) {
+        uint32_t n_blocks = ceil_div(n_per, 64);
+        ZKB_LAUNCH(ctx, (k_sum_points<F>), dim3(n_blocks, 1), 64, 0, st, pin, n_per, pout, 1u);
+        Pt* nx = pin;
+        pin = pout;
+        pout = nx;
+        n_per = n_blocks;
+      }
+      ZKB_CUDA(ctx, cudaMemcpyAsync(d_result, pin, sizeof(Pt), cudaMemcpyDeviceToDevice, st));
+      return ZKB_OK;
+    }
     const uint32_t n_buckets = g.B * g.n_sets;
     if (n_buckets > (1u << 23)) return set_err(ctx, ZKB_E_INVALID, "msm: too many buckets");
     const size_t max_entries = n * (size_t)g.W;
