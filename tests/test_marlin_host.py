@@ -60,3 +60,50 @@ def test_marlin_oracle_rejects_a_bad_witness():
         polys.update(OM.prover_third_round(st, beta))
         ok = OM.verifier_equality_check(idx, cs.input[1:], polys, alpha, *etas, beta, rng.randrange(p))
         assert ok == (not bad)
+
+
+def _csr_from_rows(cid, rows, ni):
+    import numpy as np
+    from ckb_zkp_b200.backend import CsrMatrix
+    ptr, cols, vals = [0], [], []
+    for row in rows:
+        for co, v in row:
+            cols.append(v[1] if v[0] == "in" else ni + v[1])
+            vals.append(co)
+        ptr.append(len(cols))
+    return CsrMatrix(np.asarray(ptr, dtype=np.uint32), np.asarray(cols, dtype=np.uint32), H.fr_array(cid, vals))
+
+
+@pytest.mark.parametrize("shape", ["a_denser", "b_denser", "more_constraints", "more_variables"])
+def test_matrix_preprocessing_matches_the_oracle(shape):
+    """make_matrices_square + balance_matrices + the per-row column sort (constraint_systems.rs:9-31,83-114) on the
+    CSR form == the oracle's list-of-rows restatement, for every branch: A denser than B (rows swapped until the
+    densities cross), B denser (nothing happens), more constraints than variables (padding variables), more
+    variables than constraints (empty rows), duplicate and unsorted columns inside a row."""
+    import numpy as np
+    cid = BN254
+    p = FR[cid].p
+    rng = random.Random({"a_denser": 1, "b_denser": 2, "more_constraints": 3, "more_variables": 4}[shape])
+    cs = OM.MarlinCS(p)
+    n_cons = {"more_constraints": 40, "more_variables": 6}.get(shape, 20)
+    n_vars = {"more_constraints": 5, "more_variables": 30}.get(shape, 18)
+    vs = [cs.alloc(rng.randrange(p)) for _ in range(n_vars)] + [cs.alloc_input(rng.randrange(p))] + [("in", 0)]
+    lc = lambda k: [(rng.randrange(1, p), rng.choice(vs)) for _ in range(k)]
+    for i in range(n_cons):
+        ka, kb = (rng.randrange(3, 7), rng.randrange(0, 3)) if shape == "a_denser" else (rng.randrange(0, 3), rng.randrange(2, 6))
+        cs.enforce(lc(ka), lc(kb), lc(rng.randrange(0, 4)))
+    ni, nv = len(cs.input), len(cs.input) + len(cs.witness)
+    mats = [_csr_from_rows(cid, rows, ni) for rows in (cs.a, cs.b, cs.c)]
+    (a, b, c), extra = zm.make_matrices_square(mats, nv)
+    a, b = zm.balance_matrices(a, b)
+    got = [zm.sort_rows_by_column(m) for m in (a, b, c)]
+    cs.make_matrices_square()
+    assert extra == len(cs.input) + len(cs.witness) - nv
+    for m, want_rows in zip(got, cs.matrices()):
+        assert m.n_rows == len(want_rows)
+        ptr = [0]
+        for row in want_rows:
+            ptr.append(ptr[-1] + len(row))
+        assert m.row_ptr.tolist() == ptr
+        assert m.col_idx.tolist() == [j for row in want_rows for _, j in row]
+        assert np.array_equal(m.coeff, H.fr_array(cid, [co for row in want_rows for co, _ in row]))
