@@ -12,10 +12,14 @@ MSMs, proof assembly) over one R1CS instance + assignment.
   e2e    the same through the reference-facing call with HOST buffers (zkb_groth16_prove): H2D of the
          matrices and the assignment from pinned memory and D2H of the proof inside the timed region.
   roofline      bucket-accumulation kernel (k_accumulate): algorithmic MSM bytes / measured duration.
-  cpu_baseline  the C++ restatement of the reference's CPU prover (oracle/c, arkworks-0.2 algorithms)
-                timed on this box's host cores on a bounded sample.
-`--impl reference` times that CPU restatement alone (the Rust reference cannot be built: no toolchain,
-arkworks un-vendored) and prints the same line with "impl": "reference".
+  cpu_baseline  the C++ restatement of the reference's CPU prover (oracle/c, arkworks-0.2 algorithms): ONE full
+                proof of the bench instance with the bench key on this box's host cores (no scaling), which is
+                also compared bit for bit with the GPU proof (`gpu_proof_identical_to_cpu_port`).
+  msm / ntt / sharded_proof   the rest of BASELINE's metric and configs in the same line: stand-alone G1 MSM
+                2^24 (G1-adds/s, sharded over the N ranks), Fr NTT 2^21 / 2^24, and one proof across all N ranks
+                (strong scaling; one ncclAllGather inside the library).
+`--impl reference` times that CPU restatement alone at the SAME size, one full proof per step (the Rust reference
+cannot be built: no toolchain, arkworks un-vendored), and prints the same line with "impl": "reference".
 """
 import argparse
 import json
@@ -30,7 +34,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "groth16_proofs_per_sec_bls12_381_2e20_constraints"
+METRIC = "groth16_proofs_per_sec_bls12_381_2e20_constraints"    # main() re-derives it from --log-constraints
 UNIT = "proofs/s"
 CURVE = 1   # BLS12-381
 
@@ -42,8 +46,13 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-constraints", type=int, default=20)
-    ap.add_argument("--cpu-sample-log", type=int, default=15, help="log2 constraints of the CPU baseline sample")
+    ap.add_argument("--ref-budget-s", type=float, default=1500.0, help="wall-clock budget of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="headline only: skip the msm / ntt / sharded sub-records")
+    ap.add_argument("--msm-log", type=int, default=24, help="log2 bases of the stand-alone G1 MSM (BASELINE configs[2])")
+    ap.add_argument("--msm-steps", type=int, default=5)
+    ap.add_argument("--ntt-logs", type=int, nargs="*", default=[21, 24])
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-verify", action="store_true")
     return ap.parse_args()
 
@@ -115,84 +124,330 @@ def proof_work(n_constraints):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline (oracle/c: restated arkworks-0.2 prover) -- the only place oracle/ is touched
 # ------------------------------------------------------------------------------------------------
-def cpu_prove_setup(log_n):
-    """instance + key for the CPU sample, built without the GPU (oracle fixed-base multiplication)"""
+def cpu_instance(inst):
+    """(A, B, C) as (row_ptr, col, Montgomery coeff) tuples and the Montgomery assignment, converted by the CPU
+    oracle (no GPU involved)"""
     from ckb_zkp_b200 import synth
     from oracle import cref
-    n = 1 << log_n
-    inst = synth.MimcInstance(CURVE, n)
-    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, proof_work(n)["domain"],
-                             b_zero_cols=np.arange(4, 4 + n, 2))
     to_mont = lambda ints: cref.fr_convert(CURVE, synth.ints_to_limbs(ints), True)
-    rounds = n // 2
-    consts = synth.stream_field_ints(synth.MIMC_SEED, 2, rounds, inst.p)
-    table = to_mont(consts + [1, inst.p - 1])
+    rounds = inst.n_constraints // 2
+    table = to_mont(inst.consts + [1, inst.p - 1])
     mats = []
     for which in "ABC":
         row_ptr, cols, codes, per = getattr(inst, which)
         idx = np.where(codes == 1, rounds, np.where(codes == -2, rounds + 1, np.arange(len(codes)) // per))
         mats.append((row_ptr, cols, np.ascontiguousarray(table[idx])))
-    z = to_mont(inst.z)
+    return mats, to_mont(inst.z)
+
+
+def cpu_key_points(key):
+    """the synthetic key's points k_i * G computed on the host cores (oracle fixed-base multiplication)"""
+    from ckb_zkp_b200 import synth
+    from oracle import cref
     g1, g2 = synth.generator_mont(CURVE, 1), synth.generator_mont(CURVE, 2)
     pts = lambda grp, k: cref.fixed_base_mul(CURVE, grp, g1 if grp == 1 else g2, k)
-    pk = {"a": pts(1, key.a), "b1": pts(1, key.b), "b2": pts(2, key.b), "h": pts(1, key.h), "l": pts(1, key.l),
-          "g1_singles": pts(1, np.stack([key.alpha, key.beta, key.delta]))[0],
-          "g2_singles": pts(2, np.stack([key.beta, key.delta]))[0]}
-    return inst, key, mats, z, pk
+    return {"a": pts(1, key.a), "b1": pts(1, key.b), "b2": pts(2, key.b), "h": pts(1, key.h), "l": pts(1, key.l),
+            "g1_singles": pts(1, np.stack([key.alpha, key.beta, key.delta]))[0],
+            "g2_singles": pts(2, np.stack([key.beta, key.delta]))[0]}
 
 
-def cpu_prove_time(log_n, steps, warmup, full_log):
-    """seconds per CPU proof at 2^log_n constraints, and that time scaled to 2^full_log constraints by
-    the ratio of the reference algorithm's own group-addition counts (MSM dominates; the window size
-    grows with n, so the scale factor is a little below the ratio of sizes)."""
+def cpu_prove_setup(log_n, rank=0):
+    """instance + key for the CPU arm, built without the GPU: same circuit, witness seed and key as rank `rank`
+    of the GPU arm"""
+    from ckb_zkp_b200 import synth
+    n = 1 << log_n
+    inst = synth.MimcInstance(CURVE, n, seed=synth.MIMC_SEED + rank)
+    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, proof_work(n)["domain"],
+                             b_zero_cols=np.arange(4, 4 + n, 2))
+    mats, z = cpu_instance(inst)
+    return inst, key, mats, z, cpu_key_points(key)
+
+
+def bench_rs(rank):
+    from ckb_zkp_b200 import synth
+    return synth.ints_to_limbs([0x1234567 + rank])[0], synth.ints_to_limbs([0x89ABCDE + rank])[0]
+
+
+def cpu_prove_once(inst, mats, z, pk, r, s):
+    """one pass of the reference's CPU prove path (prover.rs:148-210) on all host threads -> (seconds, proof)"""
     from oracle import cref
-    inst, key, mats, z, pk = cpu_prove_setup(log_n)
-    r = np.array([5, 0, 0, 0], dtype=np.uint64)
-    s = np.array([7, 0, 0, 0], dtype=np.uint64)
-    threads = cref.threads()
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        cref.groth16_prove(CURVE, pk, mats[0], mats[1], mats[2], z, inst.n_inputs, inst.n_aux, r, s, threads)
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    t = sum(times) / len(times)
-    scale = proof_work(1 << full_log)["ref_group_adds"] / proof_work(1 << log_n)["ref_group_adds"]
-    return t, t * scale, threads, scale
+    t0 = time.perf_counter()
+    proof = cref.groth16_prove(CURVE, pk, mats[0], mats[1], mats[2], z, inst.n_inputs, inst.n_aux, r, s, cref.threads())
+    return time.perf_counter() - t0, proof
 
 
 def run_reference(args):
+    """The reference's CPU prove path at the SAME configuration as our arm: every step is one full proof of the
+    2^log_constraints-constraint instance (no sample, no scaling factor).  The Rust reference cannot be built here
+    (no toolchain, arkworks un-vendored), so this is the C++ restatement of its algorithm (oracle/c, kind "port")
+    on all host threads.  A wall-clock budget (--ref-budget-s) trims the step count rather than being killed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import cref
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    t0 = time.perf_counter()
-    t_sample, t_full, threads, scale = cpu_prove_time(args.cpu_sample_log, steps, min(warmup, 1), args.log_constraints)
-    value = 1.0 / t_full
-    sample = ("full Groth16 prove (witness_map + 5 MSMs + assembly) at 2^%d constraints, %.3f s/proof, scaled x%.2f "
-              "to 2^%d by the reference algorithm's group-addition count" % (args.cpu_sample_log, t_sample, scale,
-                                                                             args.log_constraints))
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": warmup, "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64 (modular integer arithmetic, 255-bit Fr / 381-bit Fq)", "data": "synthetic",
-            "config": {"workload": "Groth16 prove, BLS12-381, 2^%d-constraint MiMC-chain R1CS" % args.log_constraints,
-                       "note": "restated reference CPU path (arkworks-0.2 algorithms, oracle/c/zkref.cpp); the Rust "
-                               "reference itself cannot be built in this image"},
+    t_start = time.perf_counter()
+    inst, key, mats, z, pk = cpu_prove_setup(args.log_constraints)
+    setup_s = time.perf_counter() - t_start
+    r, s = bench_rs(0)
+    threads = cref.threads()
+    times, done_warm = [], 0
+    for i in range(warmup + steps):
+        t, _ = cpu_prove_once(inst, mats, z, pk, r, s)
+        if i < warmup:
+            done_warm += 1
+        else:
+            times.append(t)
+        elapsed = time.perf_counter() - t_start
+        if elapsed + 1.5 * t > args.ref_budget_s and times:
+            break
+        if elapsed + 1.5 * t * (warmup - done_warm + 2) > args.ref_budget_s and i < warmup:
+            warmup = done_warm          # budget nearly gone during warm-up: go straight to the timed proofs
+    t_proof = sum(times) / len(times)
+    value = 1.0 / t_proof
+    sample = ("%d full Groth16 proofs (witness_map + 5 MSMs + assembly) at 2^%d constraints, %.2f s each (min %.2f, max "
+              "%.2f); no scaling; %s build of oracle/c/zkref.cpp; key built on the host in %.0f s (untimed)"
+              % (len(times), args.log_constraints, t_proof, min(times), max(times), cref.variant(), setup_s))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": done_warm, "ms_per_step": t_proof * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 (modular integer arithmetic, 255-bit Fr / 381-bit Fq)", "data": "synthetic",
+            "config": {"workload": "Groth16 prove, BLS12-381, 2^%d-constraint MiMC-chain R1CS, 1 proof per step "
+                                   "(BASELINE configs[1])" % args.log_constraints,
+                       "domain": proof_work(1 << args.log_constraints)["domain"],
+                       "note": "restated reference CPU path (arkworks-0.2 algorithms, oracle/c/zkref.cpp) on all host "
+                               "threads; the Rust reference itself cannot be built in this image"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
     emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _events(torch, n):
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)], [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def ref_msm_adds(n, bits=255):
+    """mixed + reduction additions of the reference's own MSM (ark-ec 0.2 window rule): n*W + 2*(2^c-1)*W"""
+    c = ark_window(n)
+    w = -(-bits // c)
+    return n * w + 2 * ((1 << c) - 1) * w, c, w
+
+
+def sub_sharded_proof(args, torch, ctx, world, rank, key, inst0, A, B, C, z, r, s, want, stream, flush, steps, barrier, tmax):
+    """ONE proof by all ranks (strong scaling): queries sharded over the ranks, one ncclAllGather of
+    (A_k, C_k, B2_k) inside the library, every rank ends with the same proof"""
+    t0 = time.perf_counter()
+    sharded = key.upload(ctx, CURVE, shard=(world, rank))
+    ctx.groth16_stage(sharded.pk, A, B, C, z, inst0.n_inputs, inst0.n_aux)
+    for _ in range(3):
+        ctx.groth16_prove_sharded_staged(sharded.pk, r, s)
+    ctx.sync()
+    got = ctx.groth16_fetch_proof(sharded.pk)
+    same = all(a[1] == b[1] and np.array_equal(a[0], b[0]) for a, b in zip(got, want)) if want is not None else None
+    barrier()
+    c0, l0 = ctx.collective_count, ctx.launch_count
+    st, en = _events(torch, steps)
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        barrier()                                    # a collective step: all ranks enter together
+        with torch.cuda.stream(stream):
+            st[i].record()
+            ctx.groth16_prove_sharded_staged(sharded.pk, r, s)
+            en[i].record()
+    barrier()
+    ms = tmax(sum(a.elapsed_time(b) for a, b in zip(st, en))) / steps
+    colls = (ctx.collective_count - c0) // steps
+    launches = (ctx.launch_count - l0) // steps
+    sharded.free()
+    return {"metric": "groth16_single_proof_latency_ms", "ms_per_proof": ms, "proofs_per_s": 1e3 / ms, "n_gpus": world,
+            "scaling": "strong", "identical_to_single_gpu_proof": same, "collectives_per_proof": colls,
+            "gpu_launches_per_rank": launches,
+            "how": "zkb_groth16_prove_sharded_staged: every MSM's pairs partitioned over the ranks, witness_map on every rank, "
+                   "one ncclAllGather of 3 partial points per rank, fold kernel; CUDA events, max over ranks, L2 flushed",
+            "setup_s": round(time.perf_counter() - t0, 1)}
+
+
+def sub_msm(args, torch, ctx, world, rank, stream, flush, barrier, tmax, peak):
+    """BASELINE configs[2]: stand-alone G1 MSM, BLS12-381, 2^log_n bases sharded contiguously over the ranks"""
+    from ckb_zkp_b200 import parallel, synth
+    t0 = time.perf_counter()
+    log_n = args.msm_log
+    n = 1 << log_n
+    p = synth.FR_MODULUS[CURVE]
+    lo, hi = parallel.shard_range(n, world, rank)
+    BLK = 1 << 18                       # seeded per global block so every world size sees the same data
+    gen = synth.generator_mont(CURVE, 1)
+    xs, infs, es = [], [], []
+    ssum = 0
+    for b0 in range(lo - lo % BLK, hi, BLK):
+        rng = np.random.default_rng(1000 + b0 // BLK)
+        k = synth.random_exponents(rng, BLK)
+        sc = synth.random_exponents(rng, BLK)
+        sl = slice(max(lo, b0) - b0, min(hi, b0 + BLK) - b0)
+        k, sc = k[sl], sc[sl]
+        xy, inf = ctx.fixed_base_mul(CURVE, 1, gen, k)
+        xs.append(xy); infs.append(inf); es.append(sc)
+        ssum = (ssum + sum(x * y for x, y in zip(synth.limbs_to_ints(sc), synth.limbs_to_ints(k)))) % p
+    xy, inf, s_local = np.concatenate(xs), np.concatenate(infs), np.concatenate(es)
+    shard = parallel.ShardedSrs(ctx, CURVE, 1, xy, inf, n, world, rank)
+    del xy, xs
+    d_scalars = torch.from_numpy(s_local.view(np.int64)).cuda()
+    for _ in range(3):
+        res = shard.msm_local(d_scalars.data_ptr())
+    barrier()
+    steps = args.msm_steps
+    ctx.prof_enable(True)
+    l0 = ctx.launch_count
+    st, en = _events(torch, steps)
+    for i in range(steps):
+        flush.fill_(i & 0xFF)
+        barrier()
+        with torch.cuda.stream(stream):
+            st[i].record()
+            res = shard.msm_local(d_scalars.data_ptr())       # ends with the D2H of the folded point
+            en[i].record()
+    barrier()
+    prof = ctx.prof_read()
+    ctx.prof_enable(False)
+    ms = tmax(sum(a.elapsed_time(b) for a, b in zip(st, en))) / steps
+    launches = (ctx.launch_count - l0) // steps
+    # result == (sum s_i k_i mod r) * G
+    e = torch.tensor(np.frombuffer(int(ssum).to_bytes(32, "little"), dtype=np.int64).copy(), device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        parts = [torch.zeros_like(e) for _ in range(world)]
+        dist.all_gather(parts, e)
+        ssum = sum(int.from_bytes(x.cpu().numpy().tobytes(), "little") for x in parts) % p
+    want_xy, want_inf = ctx.fixed_base_mul(CURVE, 1, gen, synth.ints_to_limbs([ssum]))
+    ok = bool(want_inf[0]) == res[1] and (res[1] or bool(np.array_equal(want_xy[0], res[0])))
+    adds, c_ref, w_ref = ref_msm_adds(n)
+    alg = n * 128.0
+    k_ms = prof["ms"] / max(prof["launches"], 1)
+    out = {"metric": "msm_g1_adds_per_sec_bls12_381_2e%d" % log_n, "value": adds / (ms * 1e-3), "unit": "G1-adds/s",
+           "n_gpus": world, "scaling": "strong", "steps": steps, "ms_per_msm": ms, "verified_in_exponent": bool(ok),
+           "g1_adds_definition": "mixed + reduction additions of the reference algorithm (ark-ec 0.2: c=%d, %d windows): "
+                                 "n*W + 2*(2^c-1)*W = %d; the simpler n*W = %d" % (c_ref, w_ref, adds, n * w_ref),
+           "how": "zkb_msm_sharded_local: bases (with window tables) and scalars resident per rank, local MSM, one "
+                  "ncclAllGather of the partial points, fold kernel, D2H of the result; CUDA events, max over ranks, L2 flushed",
+           "gpu_launches_per_rank": launches,
+           "roofline": {"bound": "hbm", "kernel": "k_accumulate (rank 0's shard)", "achieved": alg / world / (k_ms * 1e-3) / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": alg / world / (k_ms * 1e-3) / 1e9 / peak,
+                        "algorithmic_bytes_per_launch": alg / world, "avg_launch_ms": k_ms, "launches": prof["launches"]},
+           "setup_s": round(time.perf_counter() - t0, 1)}
+    shard.free()
+    del d_scalars
+    return out
+
+
+def sub_ntt(args, torch, ctx, stream, flush, peak):
+    """BASELINE configs[3] (two sizes of the sweep; tools/bench_ntt.py runs all of 2^16..2^24)"""
+    rng = np.random.default_rng(4)
+    out = []
+    for curve, name in ((1, "bls12_381"), (0, "bn254")):
+        for log_n in args.ntt_logs:
+            n = 1 << log_n
+            host = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+            host[:, 3] &= np.uint64((1 << 60) - 1)
+            d = torch.from_numpy(host.view(np.int64)).cuda()
+            orig = d.clone()
+            torch.cuda.synchronize()
+            ctx.ntt_dev(curve, d.data_ptr(), log_n)
+            ctx.ntt_dev(curve, d.data_ptr(), log_n, inverse=True)
+            ctx.sync()
+            ok = bool(torch.equal(d, orig))
+            rec = {"field": name + "_fr", "log_n": log_n, "ifft_of_fft_is_identity": ok}
+            for variant, kw in (("fft", {}), ("coset_ifft", {"inverse": True, "coset": True})):
+                for _ in range(3):
+                    ctx.ntt_dev(curve, d.data_ptr(), log_n, **kw)
+                ctx.sync()
+                steps = 5
+                st, en = _events(torch, steps)
+                for i in range(steps):
+                    flush.fill_(i)
+                    torch.cuda.synchronize()
+                    with torch.cuda.stream(stream):
+                        st[i].record()
+                        ctx.ntt_dev(curve, d.data_ptr(), log_n, **kw)
+                        en[i].record()
+                torch.cuda.synchronize()
+                ms = sum(a.elapsed_time(b) for a, b in zip(st, en)) / steps
+                alg = 2.0 * n * 32
+                rec[variant] = {"ms": ms, "butterflies_per_s": n / 2 * log_n / (ms * 1e-3),
+                                "hbm_gbs": alg / (ms * 1e-3) / 1e9, "hbm_frac": alg / (ms * 1e-3) / 1e9 / peak}
+            out.append(rec)
+            del d, orig
+    return {"metric": "fr_ntt_ms", "how": "zkb_ntt_dev in place on a resident vector, CUDA events, L2 flushed; algorithmic bytes "
+                                          "= 2 * N * 32 per transform", "sizes": out}
+
+
+def measure_traffic(args):
+    """dram__bytes_read + write of the k_accumulate launches of one serialised proof: this file re-run as a child under ncu
+    (two metrics, one replay pass each), on the same GPU after the parent released it.  Falls back to the committed capture
+    (profiles/r2_traffic.json), then to null."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    try:
+        if not os.path.exists(ncu):
+            raise RuntimeError("ncu not found")
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+               "regex:k_accumulate", "-c", "5", "--csv", sys.executable, os.path.abspath(__file__), "--traffic-child",
+               "--log-constraints", str(args.log_constraints)]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT,
+                             env=dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")).stdout
+        start = out.find('"ID"')
+        if start < 0:
+            raise RuntimeError("no ncu csv in the child's output: " + out[-300:])
+        per_launch = {}
+        for row in csv.DictReader(io.StringIO(out[start:])):
+            v = float(row["Metric Value"].replace(",", ""))
+            unit = row.get("Metric Unit", "byte").lower()
+            v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            per_launch[row["ID"]] = per_launch.get(row["ID"], 0.0) + v
+        if not per_launch:
+            raise RuntimeError("no k_accumulate launch captured")
+        vals = list(per_launch.values())
+        return sum(vals) / len(vals), "ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d k_accumulate " \
+                                      "launches of one proof, captured by this run" % len(vals)
+    except Exception as e:  # noqa: BLE001
+        try:
+            rec = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            if rec.get("log_constraints") == args.log_constraints:
+                return rec["bytes_per_launch"], "committed capture profiles/r2_traffic.json (live ncu failed: %s)" % str(e)[:120]
+        except Exception:  # noqa: BLE001
+            pass
+        return None, "unavailable: %s" % str(e)[:160]
+
+
+def traffic_child(args):
+    """one serialised proof at the bench size (the process ncu wraps; prints nothing of its own)"""
+    from ckb_zkp_b200 import synth
+    from ckb_zkp_b200.backend import Context
+    ctx = Context(0)
+    n = 1 << args.log_constraints
+    inst = synth.MimcInstance(CURVE, n)
+    A, B, C, z = inst.device_form(ctx)
+    key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, proof_work(n)["domain"], b_zero_cols=np.arange(4, 4 + n, 2))
+    params = key.upload(ctx, CURVE)
+    r, s = bench_rs(0)
+    ctx.set_serial(True)
+    ctx.groth16_stage(params.pk, A, B, C, z, inst.n_inputs, inst.n_aux)
+    ctx.groth16_prove_staged(params.pk, r, s)
+    ctx.sync()
+    params.free()
+    ctx.close()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     from ckb_zkp_b200 import synth
-    from ckb_zkp_b200.backend import Context
+    from ckb_zkp_b200.backend import Context, CsrMatrix
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -202,29 +457,41 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     ctx = Context(local)      # raises if libzkb.so or the B200 is missing: no fallback
+    ctx.comm_init_torch()     # the library's own NCCL communicator (id broadcast over torch.distributed)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def tmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     n = 1 << args.log_constraints
     work = proof_work(n)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
 
     # ---- workload: every rank proves its own witness (different MiMC seed per rank) of the same circuit shape
     t_setup = time.perf_counter()
     inst = synth.MimcInstance(CURVE, n, seed=synth.MIMC_SEED + rank)
     A, B, C, z_mont = inst.device_form(ctx)
     key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, work["domain"], b_zero_cols=np.arange(4, 4 + n, 2))
-    params = key.upload(ctx, CURVE)
+    want_cpu = world == 1 and not args.no_cpu_baseline
+    params = key.upload(ctx, CURVE, keep_host=want_cpu)
     # pinned host copies for the end-to-end path
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    from ckb_zkp_b200.backend import CsrMatrix
     Ap, Bp, Cp = [CsrMatrix(pin(m.row_ptr), pin(m.col_idx), pin(m.coeff)) for m in (A, B, C)]
     zp = pin(z_mont)
-    r = synth.ints_to_limbs([0x1234567 + rank])[0]
-    s = synth.ints_to_limbs([0x89ABCDE + rank])[0]
+    r, s = bench_rs(rank)
     setup_s = time.perf_counter() - t_setup
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
@@ -239,8 +506,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    starts, ends = _events(torch, steps)
     launches0 = ctx.launch_count
     for i in range(steps):
         flush.fill_(i & 0xFF)             # evict L2 between timed iterations (working set also exceeds L2)
@@ -269,15 +535,13 @@ def run_ours(args):
     # ---- kernel timing for the roofline figure: the same proof with every kernel on ONE stream (zkb_set_serial), so
     # the CUDA events around each bucket-accumulation launch measure the kernel, not its wait behind the other
     # four MSMs; its share of the serialised step is what the ncu launch list (profiles/) shows too
-    prof_out, serial_ms = None, None
+    prof_out, serial_ms, n_prof = None, None, min(steps, 3)
     if rank == 0:
         ctx.set_serial(True)
         ctx.groth16_prove_staged(params.pk, r, s)
         ctx.sync()
         ctx.prof_enable(True)
-        n_prof = min(steps, 3)
-        s0 = [torch.cuda.Event(enable_timing=True) for _ in range(n_prof)]
-        s1 = [torch.cuda.Event(enable_timing=True) for _ in range(n_prof)]
+        s0, s1 = _events(torch, n_prof)
         for i in range(n_prof):
             flush.fill_(i & 0xFF)
             torch.cuda.synchronize()
@@ -291,11 +555,7 @@ def run_ours(args):
         ctx.set_serial(False)
         serial_ms = sum(a.elapsed_time(b) for a, b in zip(s0, s1))
 
-    # ---- max over ranks
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = t.tolist()
+    dev_ms_max, e2e_ms_max = tmax(dev_ms), tmax(e2e_s * 1e3)
 
     # ---- full-size correctness: every proof element is a known multiple of the generator
     verified = None
@@ -304,6 +564,19 @@ def run_ours(args):
 
     h2d = zp.nbytes + sum(m.row_ptr.nbytes + m.col_idx.nbytes + m.coeff.nbytes for m in (Ap, Bp, Cp))
     d2h = 2 * 96 + 192 + 16
+
+    # ---- one proof across all ranks (strong scaling), on rank 0's instance
+    sharded_rec = None
+    if world > 1 and not args.no_sub:
+        if rank == 0:
+            inst0, A0, B0, C0, z0 = inst, Ap, Bp, Cp, zp
+        else:
+            inst0 = synth.MimcInstance(CURVE, n, seed=synth.MIMC_SEED)
+            A0, B0, C0, z0 = inst0.device_form(ctx)
+        r0, s0_ = bench_rs(0)
+        want = proof if rank == 0 else None
+        sharded_rec = sub_sharded_proof(args, torch, ctx, world, rank, key, inst0, A0, B0, C0, z0, r0, s0_, want, stream, flush,
+                                        min(steps, 10), barrier, tmax)
 
     line = None
     if rank == 0:
@@ -315,27 +588,21 @@ def run_ours(args):
                                        "step (BASELINE configs[1])" % args.log_constraints,
                            "domain": work["domain"], "msm_pairs": work["msm_pairs"],
                            "algorithmic_bytes_per_proof": work["bytes"], "l2": "flushed between timed iterations",
-                           "parallelism": "independent proofs per rank, no collective"},
+                           "parallelism": "headline value: independent proofs per rank (weak scaling, no data-path collective); "
+                                          "`sharded_proof` and `msm` below: one proof / one MSM across all ranks with one "
+                                          "ncclAllGather inside the library (strong scaling)"},
                 "e2e": {"value": world * steps / (e2e_ms_max / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks, "verified_in_exponent": verified, "setup_s": round(setup_s, 1)}
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = peaks.get("hbm_gbs", 6650.0)
+        if sharded_rec:
+            line["sharded_proof"] = sharded_rec
         if prof_out and prof_out["launches"]:
             ms = prof_out["ms"] / prof_out["launches"]
             bytes_per = prof_out["alg_bytes"] / prof_out["launches"]
             ach = bytes_per / (ms * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "kernel": "k_accumulate (Pippenger bucket accumulation)", "achieved": ach,
                                 "peak": peak, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
-                                "unit": "GB/s", "frac": ach / peak,
-                                # dram__bytes_read + write of one G1 launch (a_query MSM, 2^20 pairs) from the ncu
-                                # --set full capture in profiles/r1_accumulate_v4_ncu_full.txt; by design far above
-                                # the algorithmic bytes: the window tables are gathered once per bucket entry
-                                "traffic": 2.694e9 if args.log_constraints == 20 else None, "avg_launch_ms": ms,
+                                "unit": "GB/s", "frac": ach / peak, "traffic": None, "avg_launch_ms": ms,
                                 "launches": prof_out["launches"], "share_of_step": prof_out["ms"] / serial_ms,
                                 "timing": "CUDA events on the launching stream around each k_accumulate launch, %d proofs with "
                                           "all kernels serialised on one stream (%.2f ms per serialised proof)"
@@ -356,19 +623,42 @@ def run_ours(args):
             ach = work["bytes"] / (dev_ms_max / steps * 1e-3) / 1e9
             line["roofline"] = {"bound": "hbm", "kernel": "whole prove step", "achieved": ach, "peak": peak, "unit": "GB/s",
                                 "frac": ach / peak, "traffic": None}
+    host_points = getattr(key, "host_points", None)
     params.free()
+
+    # ---- the rest of BASELINE's metric and configs, after the proving key left the GPU
+    if not args.no_sub:
+        msm_rec = sub_msm(args, torch, ctx, world, rank, stream, flush, barrier, tmax, peak)
+        if rank == 0:
+            line["msm"] = msm_rec
+            if world == 1:
+                line["ntt"] = sub_ntt(args, torch, ctx, stream, flush, peak)
+    gpu_collectives = ctx.collective_count
     ctx.close()
     del flush
     torch.cuda.empty_cache()
 
     if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            t_sample, t_full, threads, scale = cpu_prove_time(args.cpu_sample_log, 2, 1, args.log_constraints)
-            line["cpu_baseline"] = {"value": 1.0 / t_full, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "full Groth16 prove at 2^%d constraints (%.3f s), scaled x%.2f to 2^%d by the "
-                                              "reference algorithm's group-addition count; restated arkworks-0.2 CPU "
-                                              "prover (oracle/c)" % (args.cpu_sample_log, t_sample, scale,
-                                                                     args.log_constraints)}
+        line["collectives"] = gpu_collectives
+        if world == 1 and not args.no_sub and "roofline" in line and "avg_launch_ms" in line["roofline"]:
+            traffic, how = measure_traffic(args)
+            line["roofline"]["traffic"] = traffic
+            line["roofline"]["traffic_source"] = how
+        if want_cpu and host_points is not None:
+            # one full proof of the SAME instance with the SAME key by the CPU port: the baseline, and a full-size
+            # bit-for-bit parity check of the GPU proof against the restated reference prover
+            from oracle import cref
+            mats, z_cpu = cpu_instance(inst)
+            hp = host_points
+            pk = {k: hp[k] for k in ("a", "b1", "b2", "h", "l")}
+            pk["g1_singles"], pk["g2_singles"] = hp["g1_singles"], hp["g2_singles"]
+            t_cpu, ref = cpu_prove_once(inst, mats, z_cpu, pk, r, s)
+            same = all(a[1] == b[1] and (a[1] or np.array_equal(a[0], b[0])) for a, b in zip(proof, ref))
+            line["cpu_baseline"] = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cref.threads(), "kind": "port",
+                                    "sample": "one full Groth16 proof at 2^%d constraints (the bench instance and key), "
+                                              "%.2f s, no scaling; restated arkworks-0.2 CPU prover (oracle/c, %s build)"
+                                              % (args.log_constraints, t_cpu, cref.variant())}
+            line["gpu_proof_identical_to_cpu_port"] = bool(same)
         emit(line)
     if world > 1:
         dist.barrier()
@@ -398,10 +688,13 @@ def emit(line):
 
 if __name__ == "__main__":
     a = parse()
+    METRIC = "groth16_proofs_per_sec_bls12_381_2e%d_constraints" % a.log_constraints
     sys.stdout.flush()
     REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
-    if a.impl == "reference":
+    if a.traffic_child:
+        traffic_child(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

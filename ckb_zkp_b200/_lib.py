@@ -14,6 +14,7 @@ BN254, BLS12_381 = 0, 1
 G1, G2 = 1, 2
 NTT_INVERSE, NTT_COSET = 1, 2
 SRS_PRECOMPUTE = 1
+COMM_ID_BYTES = 128
 
 OK, E_INVALID, E_CUDA, E_TOO_LARGE, E_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -58,6 +59,28 @@ SIGNATURES = {
                                   c_void_p, c_size_t, c_size_t]),
     "zkb_groth16_prove_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "zkb_groth16_fetch_proof": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zkb_comm_unique_id": (c_int, [c_void_p, c_void_p]),
+    "zkb_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "zkb_comm_destroy": (None, [c_void_p]),
+    "zkb_comm_rank": (c_int, [c_void_p]),
+    "zkb_comm_size": (c_int, [c_void_p]),
+    "zkb_comm_collectives": (c_u64, [c_void_p]),
+    "zkb_srs_upload_shard": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_size_t, c_size_t, c_uint,
+                                     ctypes.POINTER(c_void_p)]),
+    "zkb_msm_sharded": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p, c_void_p]),
+    "zkb_msm_sharded_local": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zkb_partial_bytes": (c_size_t, [c_int, c_int]),
+    "zkb_msm_partial": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_void_p]),
+    "zkb_msm_fold": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zkb_groth16_pk_create_sharded": (c_int, [c_void_p, c_int] + [c_void_p, c_void_p, c_size_t] * 5
+                                      + [c_void_p, c_void_p, c_int, c_int, ctypes.POINTER(c_void_p)]),
+    "zkb_groth16_prove_sharded": (c_int, [c_void_p, c_void_p, ctypes.POINTER(Csr), ctypes.POINTER(Csr), ctypes.POINTER(Csr),
+                                          c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zkb_groth16_prove_sharded_staged": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zkb_groth16_partial_bytes": (c_size_t, [c_int]),
+    "zkb_groth16_prove_partial": (c_int, [c_void_p, c_void_p, ctypes.POINTER(Csr), ctypes.POINTER(Csr), ctypes.POINTER(Csr),
+                                          c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "zkb_groth16_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zkb_fixed_base_mul": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zkb_fr_convert": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "zkb_poly_div_linear": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),

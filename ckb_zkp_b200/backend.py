@@ -214,6 +214,96 @@ class Context:
                                                 _ptr(oinf)))
         return out, oinf
 
+    # -- multi-GPU (one process per GPU; NCCL inside the library) -----------------------------------
+    def comm_unique_id(self):
+        """rank 0: the 128-byte NCCL id the host then distributes (torch.distributed broadcast, MPI, a file)"""
+        buf = np.zeros(_lib.COMM_ID_BYTES, dtype=np.uint8)
+        self._check(self.lib.zkb_comm_unique_id(self.handle, _ptr(buf)))
+        return buf
+
+    def comm_init(self, n_ranks, rank, unique_id=None):
+        """collective: every rank calls it with the same id (None only for n_ranks == 1)"""
+        uid = None if unique_id is None else np.ascontiguousarray(unique_id, dtype=np.uint8).reshape(_lib.COMM_ID_BYTES)
+        self._check(self.lib.zkb_comm_init(self.handle, n_ranks, rank, _ptr(uid)))
+
+    def comm_init_torch(self):
+        """convenience for hosts that already run torch.distributed: broadcast the id over the default process
+        group (the rendezvous only -- the data path is the library's own ncclAllGather)"""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            self.comm_init(1, 0)
+            return 1, 0
+        world, rank = dist.get_world_size(), dist.get_rank()
+        on_gpu = dist.get_backend() == "nccl"
+        t = torch.zeros(_lib.COMM_ID_BYTES, dtype=torch.uint8, device="cuda" if on_gpu else "cpu")
+        if rank == 0:
+            t.copy_(torch.from_numpy(self.comm_unique_id()))
+        dist.broadcast(t, 0)
+        self.comm_init(world, rank, t.cpu().numpy())
+        return world, rank
+
+    def comm_destroy(self):
+        self.lib.zkb_comm_destroy(self.handle)
+
+    @property
+    def comm_size(self):
+        return int(self.lib.zkb_comm_size(self.handle))
+
+    @property
+    def comm_rank(self):
+        return int(self.lib.zkb_comm_rank(self.handle))
+
+    @property
+    def collective_count(self):
+        return int(self.lib.zkb_comm_collectives(self.handle))
+
+    def srs_upload_shard(self, curve, group, xy_local, inf_local, global_lo, global_n, precompute=True):
+        xy = np.ascontiguousarray(xy_local, dtype=np.uint64)
+        w = point_words(curve, group)
+        if xy.ndim != 2 or xy.shape[1] != w:
+            raise ValueError("bases must be uint64[n, %d]" % w)
+        n = xy.shape[0]
+        inf = np.zeros(n, dtype=np.uint8) if inf_local is None else np.ascontiguousarray(inf_local, dtype=np.uint8)
+        if inf.shape != (n,):
+            raise ValueError("infinity flags must be uint8[n]")
+        h = ctypes.c_void_p()
+        self._check(self.lib.zkb_srs_upload_shard(self.handle, curve, group, _ptr(xy), _ptr(inf), n, global_lo, global_n,
+                                                  _lib.SRS_PRECOMPUTE if precompute else 0, ctypes.byref(h)))
+        return Srs(self, h, curve, group, n)
+
+    def msm_sharded(self, srs_shard, scalars, base_offset=0, mont=False):
+        """collective; every rank passes the same full-length scalars and gets the same (xy, is_identity)"""
+        scalars = _fr(scalars)
+        out = np.zeros(point_words(srs_shard.curve, srs_shard.group), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_sharded(self.handle, srs_shard.handle, base_offset, _addr(scalars), scalars.shape[0],
+                                             1 if mont else 0, _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
+    def msm_sharded_local(self, srs_shard, d_scalars_ptr, n_local):
+        """collective; canonical scalars of this rank's pairs already in device memory"""
+        out = np.zeros(point_words(srs_shard.curve, srs_shard.group), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_sharded_local(self.handle, srs_shard.handle, ctypes.c_void_p(d_scalars_ptr), n_local,
+                                                   _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
+    def msm_partial(self, srs_shard, scalars, base_offset=0, mont=False):
+        """this rank's partial point as opaque bytes (for a caller-supplied transport)"""
+        scalars = _fr(scalars)
+        out = np.zeros(int(self.lib.zkb_partial_bytes(srs_shard.curve, srs_shard.group)), dtype=np.uint8)
+        self._check(self.lib.zkb_msm_partial(self.handle, srs_shard.handle, base_offset, _addr(scalars), scalars.shape[0],
+                                             1 if mont else 0, _ptr(out)))
+        return out
+
+    def msm_fold(self, curve, group, partials):
+        """fold of the ranks' partials (uint8[count, partial_bytes]) in index order -> (xy, is_identity)"""
+        partials = np.ascontiguousarray(partials, dtype=np.uint8)
+        out = np.zeros(point_words(curve, group), dtype=np.uint64)
+        oinf = np.zeros(1, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_fold(self.handle, curve, group, _ptr(partials), partials.shape[0], _ptr(out), _ptr(oinf)))
+        return out, bool(oinf[0])
+
     # -- NTT ----------------------------------------------------------------------------------
     def ntt(self, curve, data, log_n, inverse=False, coset=False):
         """In-place transform of uint64[2^log_n, 4] (Montgomery), natural order in and out."""
@@ -316,8 +406,9 @@ class Context:
                                            _ptr(z), n_inputs, n_aux, _ptr(h)))
         return h
 
-    def groth16_pk(self, curve, a, b_g1, b_g2, h, l, g1_singles, g2_singles):
-        """a, b_g1, b_g2, h, l: (xy, inf) pairs; g1_singles = [alpha, beta, delta], g2_singles = [beta, delta]."""
+    def groth16_pk(self, curve, a, b_g1, b_g2, h, l, g1_singles, g2_singles, shard=None):
+        """a, b_g1, b_g2, h, l: (xy, inf) pairs; g1_singles = [alpha, beta, delta], g2_singles = [beta, delta].
+        shard = (n_ranks, rank): keep only this rank's slice of the MSM pairs resident (zkb_groth16_pk_create_sharded)."""
         args = []
         for (xy, inf), group in ((a, G1), (b_g1, G1), (b_g2, G2), (h, G1), (l, G1)):
             xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, point_words(curve, group))
@@ -331,7 +422,11 @@ class Context:
         for xy, inf in args:
             flat += [_ptr(xy), _ptr(inf), xy.shape[0]]
         hdl = ctypes.c_void_p()
-        self._check(self.lib.zkb_groth16_pk_create(self.handle, curve, *flat, _ptr(s1), _ptr(s2), ctypes.byref(hdl)))
+        if shard is None:
+            self._check(self.lib.zkb_groth16_pk_create(self.handle, curve, *flat, _ptr(s1), _ptr(s2), ctypes.byref(hdl)))
+        else:
+            self._check(self.lib.zkb_groth16_pk_create_sharded(self.handle, curve, *flat, _ptr(s1), _ptr(s2), int(shard[0]),
+                                                               int(shard[1]), ctypes.byref(hdl)))
         return ProvingKey(self, hdl, curve)
 
     def _proof_arrays(self, curve):
@@ -364,6 +459,44 @@ class Context:
         r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
         s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
         self._check(self.lib.zkb_groth16_prove_staged(self.handle, pk.handle, _ptr(r), _ptr(s)))
+
+    def groth16_prove_sharded(self, pk, A, B, C, z_mont, n_inputs, n_aux, r, s):
+        """collective: ONE proof by all ranks (same arguments and result on every rank as groth16_prove)"""
+        z = _fr(z_mont, "assignment")
+        if z.shape[0] != n_inputs + n_aux:
+            raise ValueError("assignment length != n_inputs + n_aux")
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        buf, inf, w1, w2 = self._proof_arrays(pk.curve)
+        self._check(self.lib.zkb_groth16_prove_sharded(self.handle, pk.handle, ctypes.byref(A.c), ctypes.byref(B.c),
+                                                       ctypes.byref(C.c), _ptr(z), n_inputs, n_aux, _ptr(r), _ptr(s),
+                                                       _ptr(buf), _ptr(inf)))
+        return self._split_proof(buf, inf, w1, w2)
+
+    def groth16_prove_sharded_staged(self, pk, r, s):
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        self._check(self.lib.zkb_groth16_prove_sharded_staged(self.handle, pk.handle, _ptr(r), _ptr(s)))
+
+    def groth16_prove_partial(self, pk, A, B, C, z_mont, n_inputs, n_aux, r, s):
+        """this rank's (A_k, C_k, B2_k) as opaque bytes (caller-supplied transport / single-GPU tests)"""
+        z = _fr(z_mont, "assignment")
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        out = np.zeros(int(self.lib.zkb_groth16_partial_bytes(pk.curve)), dtype=np.uint8)
+        self._check(self.lib.zkb_groth16_prove_partial(self.handle, pk.handle, ctypes.byref(A.c), ctypes.byref(B.c),
+                                                       ctypes.byref(C.c), _ptr(z), n_inputs, n_aux, _ptr(r), _ptr(s),
+                                                       _ptr(out)))
+        return out
+
+    def groth16_fold(self, pk, partials, r, s):
+        partials = np.ascontiguousarray(partials, dtype=np.uint8)
+        r = np.ascontiguousarray(r, dtype=np.uint64).reshape(4)
+        s = np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
+        buf, inf, w1, w2 = self._proof_arrays(pk.curve)
+        self._check(self.lib.zkb_groth16_fold(self.handle, pk.handle, _ptr(partials), partials.shape[0], _ptr(r), _ptr(s),
+                                              _ptr(buf), _ptr(inf)))
+        return self._split_proof(buf, inf, w1, w2)
 
     def groth16_fetch_proof(self, pk):
         buf, inf, w1, w2 = self._proof_arrays(pk.curve)

@@ -103,6 +103,7 @@ void zkb_destroy(zkb_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  zkb_comm_destroy(ctx);
   groth16_free_stage(ctx);
   ntt_free_domains(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -176,6 +177,7 @@ int zkb_srs_upload(zkb_ctx* ctx, int curve, int group, const uint64_t* xy_mont, 
   zkb_srs* srs = new zkb_srs();
   srs->ctx = ctx; srs->curve = curve; srs->group = group; srs->n = n;
   srs->table = nullptr; srs->inf = nullptr;
+  srs->global_lo = 0; srs->global_n = n;
   int rc = ops->srs_build(ctx, srs, xy_mont, inf, flags);
   if (rc != ZKB_OK) {
     zkb_srs_free(srs);
@@ -194,6 +196,20 @@ void zkb_srs_free(zkb_srs* srs) {
 }
 
 size_t zkb_srs_len(const zkb_srs* srs) { return srs ? srs->n : 0; }
+
+int zkb_srs_upload_shard(zkb_ctx* ctx, int curve, int group, const uint64_t* xy_mont_local, const uint8_t* inf_local,
+                         size_t n_local, size_t global_lo, size_t global_n, unsigned flags, zkb_srs** out) {
+  if (!ctx || !out) return ZKB_E_INVALID;
+  if (global_lo > global_n || n_local > global_n - global_lo) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return set_err(ctx, ZKB_E_INVALID, "srs_upload_shard: [%zu, %zu) outside the logical SRS of %zu bases", global_lo,
+                   global_lo + n_local, global_n);
+  }
+  ZKB_TRY(zkb_srs_upload(ctx, curve, group, xy_mont_local, inf_local, n_local, flags, out));
+  (*out)->global_lo = global_lo;
+  (*out)->global_n = global_n;
+  return ZKB_OK;
+}
 
 // ---- MSM -----------------------------------------------------------------------------------
 static int msm_host(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
@@ -231,6 +247,115 @@ int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void
   if (n > avail) n = avail;
   return group_ops(srs->curve, srs->group)
       ->msm_to_host(ctx, srs, base_offset, (const uint32_t*)d_scalars_canonical, n, 0, out_xy, out_inf);
+}
+
+// ---- sharded MSM (one process per GPU) ---------------------------------------------------------
+// This rank's partial of multi_scalar_mul(&bases[base_offset .. base_offset + n), &scalars[..n)) over the LOGICAL
+// SRS: the pairs whose base lies in this rank's shard [global_lo, global_lo + srs->n).  `scalars` points at the full
+// n-element array (host or device); only the local slice is read.  Result: one XYZZ point in d_partial.
+static int msm_shard_partial(zkb_ctx* ctx, cudaStream_t st, Scratch& ws, const zkb_srs* srs, size_t base_offset,
+                             const uint64_t* scalars, size_t n, int mont, void* d_partial) {
+  size_t avail = base_offset <= srs->global_n ? srs->global_n - base_offset : 0;
+  if (n > avail) n = avail;                                  // zip semantics of multi_scalar_mul
+  const size_t lo = srs->global_lo, hi = srs->global_lo + srs->n;
+  size_t g0 = base_offset > lo ? base_offset : lo;
+  size_t g1 = base_offset + n < hi ? base_offset + n : hi;
+  size_t n_loc = g1 > g0 ? g1 - g0 : 0;
+  const GroupOps* ops = group_ops(srs->curve, srs->group);
+  uint32_t* d_scalars;
+  ZKB_TRY(ws.alloc(&d_scalars, n_loc * 8));
+  if (n_loc)
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_scalars, scalars + 4 * (g0 - base_offset), n_loc * 32, cudaMemcpyDefault, st));
+  return ops->msm_run(ctx, st, srs, n_loc ? g0 - lo : 0, d_scalars, n_loc, mont, d_partial);
+}
+
+// partial (device) -> all-gather -> fold -> host
+static int msm_gather_fold(zkb_ctx* ctx, cudaStream_t st, Scratch& ws, const GroupOps* ops, const void* d_partial,
+                           uint64_t* out_xy, uint8_t* out_inf) {
+  void* d_all;
+  ZKB_TRY(comm_gather_buffer(ctx, ops->xyzz_bytes * (size_t)ctx->n_ranks, &d_all));
+  ZKB_TRY(comm_allgather(ctx, st, d_partial, d_all, ops->xyzz_bytes));
+  uint8_t *d_aff, *d_inf;
+  ZKB_TRY(ws.alloc(&d_aff, ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_inf, 16));
+  ZKB_TRY(ops->fold(ctx, st, d_all, (uint32_t)ctx->n_ranks, (uint32_t)ops->xyzz_bytes, nullptr, d_aff, d_inf));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, 1, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+int zkb_msm_partial(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+                    int scalars_mont, void* partial_out) {
+  if (!ctx || !srs || !partial_out || (n && !scalars)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm: srs belongs to another context");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  const GroupOps* ops = group_ops(srs->curve, srs->group);
+  Scratch ws(ctx, st);
+  uint8_t* d_partial;
+  ZKB_TRY(ws.alloc(&d_partial, ops->xyzz_bytes));
+  ZKB_TRY(msm_shard_partial(ctx, st, ws, srs, base_offset, scalars, n, scalars_mont, d_partial));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(partial_out, d_partial, ops->xyzz_bytes, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+size_t zkb_partial_bytes(int curve, int group) {
+  const GroupOps* ops = group_ops(curve, group);
+  return ops ? ops->xyzz_bytes : 0;
+}
+
+int zkb_msm_fold(zkb_ctx* ctx, int curve, int group, const void* partials, size_t count, uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !partials || !out_xy || !out_inf || count == 0 || count > 4096) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const GroupOps* ops = group_ops(curve, group);
+  if (!ops) return set_err(ctx, ZKB_E_INVALID, "msm_fold: unknown curve %d / group %d", curve, group);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint8_t *d_all, *d_aff, *d_inf;
+  ZKB_TRY(ws.alloc(&d_all, ops->xyzz_bytes * count));
+  ZKB_TRY(ws.alloc(&d_aff, ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_inf, 16));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_all, partials, ops->xyzz_bytes * count, cudaMemcpyDefault, st));
+  ZKB_TRY(ops->fold(ctx, st, d_all, (uint32_t)count, (uint32_t)ops->xyzz_bytes, nullptr, d_aff, d_inf));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, 1, cudaMemcpyDeviceToHost, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
+int zkb_msm_sharded(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uint64_t* scalars, size_t n,
+                    int scalars_mont, uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !srs || !out_xy || !out_inf || (n && !scalars)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm: srs belongs to another context");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  const GroupOps* ops = group_ops(srs->curve, srs->group);
+  Scratch ws(ctx, st);
+  uint8_t* d_partial;
+  ZKB_TRY(ws.alloc(&d_partial, ops->xyzz_bytes));
+  ZKB_TRY(msm_shard_partial(ctx, st, ws, srs, base_offset, scalars, n, scalars_mont, d_partial));
+  return msm_gather_fold(ctx, st, ws, ops, d_partial, out_xy, out_inf);
+}
+
+int zkb_msm_sharded_local(zkb_ctx* ctx, const zkb_srs* srs, const void* d_scalars_local, size_t n_local,
+                          uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || !srs || !out_xy || !out_inf || (n_local && !d_scalars_local)) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (srs->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm: srs belongs to another context");
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  const GroupOps* ops = group_ops(srs->curve, srs->group);
+  if (n_local > srs->n) n_local = srs->n;
+  Scratch ws(ctx, st);
+  uint8_t* d_partial;
+  ZKB_TRY(ws.alloc(&d_partial, ops->xyzz_bytes));
+  ZKB_TRY(ops->msm_run(ctx, st, srs, 0, (const uint32_t*)d_scalars_local, n_local, 0, d_partial));
+  return msm_gather_fold(ctx, st, ws, ops, d_partial, out_xy, out_inf);
 }
 
 // ---- NTT -----------------------------------------------------------------------------------

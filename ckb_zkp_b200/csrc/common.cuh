@@ -52,6 +52,13 @@ struct zkb_ctx {
   std::vector<cudaEvent_t> prof_events;   // start/stop pairs
   size_t prof_used = 0;
   double prof_alg_bytes = 0;
+  // multi-GPU: one process per GPU, this ctx is rank `rank` of `n_ranks` (comm.cu); comm == nullptr until
+  // zkb_comm_init -- the sharded entry points then fail instead of silently computing a partial result
+  void* comm = nullptr;       // ncclComm_t
+  int n_ranks = 1, rank = 0;
+  void* gather = nullptr;     // device receive buffer of the partial-point all-gather
+  size_t gather_bytes = 0;
+  uint64_t collectives = 0;   // all-gathers enqueued so far (bench.py reports it)
 };
 
 namespace zkb {
@@ -150,6 +157,11 @@ inline int on_bulk_stream(zkb_ctx* ctx, cudaStream_t st, Fn enqueue) {
   ZKB_CUDA(ctx, cudaStreamWaitEvent(st, e1, 0));
   return ZKB_OK;
 }
+
+// comm.cu: all-gather `bytes` bytes per rank from d_send into d_recv (n_ranks * bytes, rank order) on `st`;
+// with n_ranks == 1 a device-to-device copy
+int comm_allgather(zkb_ctx* ctx, cudaStream_t st, const void* d_send, void* d_recv, size_t bytes);
+int comm_gather_buffer(zkb_ctx* ctx, size_t bytes, void** out);
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 inline unsigned ceil_log2(size_t n) {

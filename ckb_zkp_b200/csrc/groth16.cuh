@@ -11,6 +11,14 @@ struct zkb_pk {
   zkb_srs *a, *b_g1, *b_g2, *h, *l;
   void* g1_singles;   // device Affine<Fq>[3]: alpha, beta, delta
   void* g2_singles;   // device Affine<Fq2>[2]: beta, delta
+  // Sharded key (zkb_groth16_pk_create_sharded): every srs holds only this rank's slice of the MSM pairs
+  // (a / b_g1 / b_g2: query[1 + lo .. 1 + hi) against assignment[lo .. hi); h, l: query[lo .. hi)), index 0 of
+  // the three coefficient queries lives in q0_*.  Order of the arrays: a, b_g1, b_g2, h, l.
+  bool sharded = false;
+  int n_ranks = 1, rank = 0;
+  size_t pair_lo[5] = {0, 0, 0, 0, 0}, pair_n[5] = {0, 0, 0, 0, 0};
+  void* q0_g1 = nullptr;    // device Affine<Fq>[2]: a_query[0], b_g1_query[0]
+  void* q0_g2 = nullptr;    // device Affine<Fq2>[1]: b_g2_query[0]
 };
 
 namespace zkb {
@@ -35,6 +43,7 @@ struct Groth16Stage {
   DevBuf z_repr;    // Fr[n_inputs + n_aux - 1] canonical (skips ONE)
   DevBuf va, vb, vc, scratch;   // Fr[N] each
   void* results = nullptr;   // device block holding MSM results and the proof (layout in groth16_impl.cuh)
+  void* shard = nullptr;     // device block of the sharded prove path (G16Shard in groth16_impl.cuh)
   void* scal = nullptr;      // device Fr[4]: r, s, r*s (canonical), spare
   bool staged = false;
   // matrices whose upload is deferred into prove_staged (host pointers, valid for the duration of zkb_groth16_prove)
@@ -49,6 +58,12 @@ struct Groth16Ops {
   int (*fetch_proof)(zkb_ctx*, const zkb_pk*, uint64_t*, uint8_t*);
   int (*fetch_h)(zkb_ctx*, uint64_t*);
   size_t g1_affine_bytes, g2_affine_bytes;
+  // sharded prove path: this rank's partial (device, stage->shard), then gather + fold into the proof
+  int (*prove_partial_staged)(zkb_ctx*, const zkb_pk*, const uint64_t*, const uint64_t*);
+  int (*fetch_partial)(zkb_ctx*, void* partial_out);
+  int (*fold_partials)(zkb_ctx*, const zkb_pk*, const void* partials_host_or_null, size_t count, const uint64_t*,
+                       const uint64_t*, bool recompute_fixed);
+  size_t partial_bytes;
 };
 const Groth16Ops* groth16_ops(int curve);
 void groth16_free_stage(zkb_ctx* ctx);

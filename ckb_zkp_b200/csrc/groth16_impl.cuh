@@ -176,6 +176,117 @@ __global__ void k_g16_finish(G16Results<Fq, Fq2>* res, unsigned first) {
 }
 
 // ------------------------------------------------------------------------------------------
+// sharded proof (one process per GPU): every rank owns a slice of the pairs of each of the five MSMs.
+// With A_k, B1_k, B2_k, L_k, H_k the partial sums of rank k, the proof of prover.rs:164-210 is
+//   g_a  = Fa  + sum_k A_k                       Fa  = r*delta + a_query[0] + alpha_g1
+//   g2_b = Fb2 + sum_k B2_k                      Fb2 = s*delta_g2 + b_g2_query[0] + beta_g2
+//   g_c  = s*Fa + r*Fb1 - r*s*delta + sum_k C_k  Fb1 = s*delta + b_g1_query[0] + beta_g1
+//   C_k  = s*A_k + r*B1_k + L_k + H_k
+// (the r == 0 guard of prover.rs:170 only zeroes r*g1_b, which r = 0 does anyway).  The scalar multiplications
+// by r and s are applied to the rank's own partials while its H / L accumulations still run, so after the ONE
+// all-gather of (A_k, C_k, B2_k) only <= n_ranks additions and one inversion per proof element remain.
+// ------------------------------------------------------------------------------------------
+template <class Fq, class Fq2>
+struct G16Partial {         // what one rank contributes to the all-gather
+  XYZZ<Fq> a, c;
+  XYZZ<Fq2> b2;
+};
+template <class Fq, class Fq2>
+struct G16Shard {
+  G16Partial<Fq, Fq2> part;
+  XYZZ<Fq> msm_b1, msm_h, msm_l;   // local partial sums that only feed part.c
+  XYZZ<Fq> s_a, r_b1;              // s * A_k, r * B1_k
+  XYZZ<Fq> fa, s_fa, r_fb1;        // rank-independent terms
+  XYZZ<Fq2> fb2;
+};
+
+// after k_g16_scalars: block 0: fa, s*fa   block 1: r*fb1   block 2: fb2
+template <class FrP, class Fq, class Fq2>
+__global__ void k_g16_fixed(const Fp<FrP>* scal, const Affine<Fq>* q0_g1, const Affine<Fq2>* q0_g2,
+                            const Affine<Fq>* g1_singles, const Affine<Fq2>* g2_singles,
+                            const G16Results<Fq, Fq2>* res, G16Shard<Fq, Fq2>* sh) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x) return;
+  Fr r = scal[0], s = scal[1];
+  if (blockIdx.x == 0) {
+    XYZZ<Fq> g = ld_vec_rw(&res->r_delta);
+    pt_madd(g, q0_g1[0], false);
+    pt_madd(g, g1_singles[0], false);    // alpha_g1
+    st_vec(&sh->fa, g);
+    st_vec(&sh->s_fa, XYZZ<Fq>::mul_limbs(g, s.v, Fr::N));
+  }
+  if (blockIdx.x == 1) {
+    XYZZ<Fq> g = ld_vec_rw(&res->s_delta);
+    pt_madd(g, q0_g1[1], false);
+    pt_madd(g, g1_singles[1], false);    // beta_g1
+    st_vec(&sh->r_fb1, XYZZ<Fq>::mul_limbs(g, r.v, Fr::N));
+  }
+  if (blockIdx.x == 2) {
+    XYZZ<Fq2> g = ld_vec_rw(&res->s_delta2);
+    pt_madd(g, q0_g2[0], false);
+    pt_madd(g, g2_singles[0], false);    // beta_g2
+    st_vec(&sh->fb2, g);
+  }
+}
+// block 0: s * A_k   block 1: r * B1_k
+template <class FrP, class Fq, class Fq2>
+__global__ void k_g16_local_mul(const Fp<FrP>* scal, G16Shard<Fq, Fq2>* sh) {
+  using Fr = Fp<FrP>;
+  if (threadIdx.x) return;
+  Fr r = scal[0], s = scal[1];
+  if (blockIdx.x == 0) { XYZZ<Fq> p = ld_vec_rw(&sh->part.a); st_vec(&sh->s_a, XYZZ<Fq>::mul_limbs(p, s.v, Fr::N)); }
+  if (blockIdx.x == 1) { XYZZ<Fq> p = ld_vec_rw(&sh->msm_b1); st_vec(&sh->r_b1, XYZZ<Fq>::mul_limbs(p, r.v, Fr::N)); }
+}
+// C_k = s*A_k + r*B1_k + L_k + H_k
+template <class Fq, class Fq2>
+__global__ void k_g16_local_c(G16Shard<Fq, Fq2>* sh) {
+  if (threadIdx.x | blockIdx.x) return;
+  XYZZ<Fq> g = ld_vec_rw(&sh->s_a);
+  XYZZ<Fq> t = ld_vec_rw(&sh->r_b1);
+  pt_add(g, t);
+  t = ld_vec_rw(&sh->msm_l);
+  pt_add(g, t);
+  t = ld_vec_rw(&sh->msm_h);
+  pt_add(g, t);
+  st_vec(&sh->part.c, g);
+}
+// fold the gathered partials in rank order, add the rank-independent terms, into_affine  (prover.rs:206-210)
+template <class Fq, class Fq2>
+__global__ void k_g16_fold_finish(const G16Partial<Fq, Fq2>* __restrict__ parts, uint32_t count,
+                                  const G16Shard<Fq, Fq2>* __restrict__ sh, G16Results<Fq, Fq2>* res) {
+  if (threadIdx.x) return;
+  if (blockIdx.x == 0) {
+    XYZZ<Fq> g = ld_vec_rw(&sh->fa);
+    for (uint32_t k = 0; k < count; k++) { XYZZ<Fq> t = ld_vec_rw(&parts[k].a); pt_add(g, t); }
+    Affine<Fq> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_a, a);
+    res->inf[0] = g.is_inf();
+  }
+  if (blockIdx.x == 1) {
+    XYZZ<Fq2> g = ld_vec_rw(&sh->fb2);
+    for (uint32_t k = 0; k < count; k++) { XYZZ<Fq2> t = ld_vec_rw(&parts[k].b2); pt_add(g, t); }
+    Affine<Fq2> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_b, a);
+    res->inf[1] = g.is_inf();
+  }
+  if (blockIdx.x == 2) {
+    XYZZ<Fq> g = ld_vec_rw(&sh->s_fa);
+    XYZZ<Fq> t = ld_vec_rw(&sh->r_fb1);
+    pt_add(g, t);
+    t = ld_vec_rw(&res->rs_delta);
+    t.neg_in_place();
+    pt_add(g, t);
+    for (uint32_t k = 0; k < count; k++) { t = ld_vec_rw(&parts[k].c); pt_add(g, t); }
+    Affine<Fq> a;
+    pt_to_affine(a, g);
+    st_vec(&res->proof_c, a);
+    res->inf[2] = g.is_inf();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 template <class FrP, class FqP, int CURVE>
@@ -184,6 +295,8 @@ struct Groth16Impl {
   using Fq = Fp<FqP>;
   using Fq2 = Fp2<FqP>;
   using Res = G16Results<Fq, Fq2>;
+  using Part = G16Partial<Fq, Fq2>;
+  using Shard = G16Shard<Fq, Fq2>;
 
   static int ensure(zkb_ctx* ctx, DevBuf* b, size_t bytes) {
     if (b->p && b->cap >= bytes) return ZKB_OK;
@@ -378,9 +491,123 @@ struct Groth16Impl {
     return ZKB_OK;
   }
 
+  // ---- sharded path ------------------------------------------------------------------------
+  // this rank's partial (A_k, C_k, B2_k) -> stage->shard->part; everything enqueued, nothing synchronised
+  static int prove_partial_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t* r, const uint64_t* sc) {
+    Groth16Stage* s = ctx->stage;
+    if (!s || !s->staged || s->curve != CURVE) return set_err(ctx, ZKB_E_INVALID, "groth16: nothing staged");
+    if (!pk || pk->curve != CURVE || pk->ctx != ctx || !pk->sharded)
+      return set_err(ctx, ZKB_E_INVALID, "groth16: not a sharded proving key of this context");
+    if (!r || !sc) return set_err(ctx, ZKB_E_INVALID, "groth16: null r/s");
+    cudaStream_t st = ctx->main;
+    cudaStream_t side[kNumSideStreams];
+    for (int i = 0; i < kNumSideStreams; i++) side[i] = ctx->serial ? st : ctx->side[i];
+    const GroupOps* g1 = group_ops(CURVE, ZKB_G1);
+    const GroupOps* g2 = group_ops(CURVE, ZKB_G2);
+    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, sizeof(Shard)));
+    Res* res = (Res*)s->results;
+    Shard* sh = (Shard*)s->shard;
+    Fr* scal = (Fr*)s->scal;
+    Fr r_val, s_val;
+    memcpy(r_val.v, r, 32);
+    memcpy(s_val.v, sc, 32);
+    ZKB_TRY(fork_streams(ctx, 1));
+    ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, side[0], r_val, s_val, scal, (const Affine<Fq>*)pk->g1_singles,
+               (const Affine<Fq2>*)pk->g2_singles, res);
+    ZKB_LAUNCH(ctx, (k_g16_fixed<FrP, Fq, Fq2>), 3, 32, 0, side[0], (const Fr*)scal, (const Affine<Fq>*)pk->q0_g1,
+               (const Affine<Fq2>*)pk->q0_g2, (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles,
+               (const Res*)res, sh);
+    const size_t n_assign = s->n_inputs - 1 + s->n_aux;
+    ZKB_TRY(fr_convert_dev(ctx, st, CURVE, (const Fr*)s->z.p + 1, s->z_repr.p, n_assign, 0));
+    const uint32_t* zr = (const uint32_t*)s->z_repr.p;
+    // local pair range of MSM `which` against a scalar vector of `avail` elements
+    auto local_n = [&](int which, size_t avail) -> size_t {
+      size_t lo = pk->pair_lo[which], hi = lo + pk->pair_n[which];
+      if (hi > avail) hi = avail;
+      return hi > lo ? hi - lo : 0;
+    };
+    ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+    for (int i = 1; i <= 5; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(side[i], ctx->ev_fork, 0));
+    ZKB_TRY(g2->msm_run(ctx, side[1], pk->b_g2, 0, zr + pk->pair_lo[2] * Fr::N, local_n(2, n_assign), 0, &sh->part.b2));
+    ZKB_TRY(g1->msm_run(ctx, side[2], pk->a, 0, zr + pk->pair_lo[0] * Fr::N, local_n(0, n_assign), 0, &sh->part.a));
+    ZKB_TRY(g1->msm_run(ctx, side[4], pk->b_g1, 0, zr + pk->pair_lo[1] * Fr::N, local_n(1, n_assign), 0, &sh->msm_b1));
+    for (int i : {0, 2, 4}) {
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
+      ZKB_CUDA(ctx, cudaStreamWaitEvent(side[5], ctx->ev_join[i], 0));
+    }
+    ZKB_LAUNCH(ctx, (k_g16_local_mul<FrP, Fq, Fq2>), 2, 32, 0, side[5], (const Fr*)scal, sh);
+    if (s->pending[0]) {
+      ZKB_TRY(upload_csr(ctx, st, &s->A, s->pending[0]));
+      ZKB_TRY(upload_csr(ctx, st, &s->B, s->pending[1]));
+      ZKB_TRY(upload_csr(ctx, st, &s->C, s->pending[2]));
+      s->pending[0] = s->pending[1] = s->pending[2] = nullptr;
+    }
+    ZKB_TRY(compute_h(ctx, st));       // every rank computes the whole h (7 transforms), then multiplies its slice
+    ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p + pk->pair_lo[3] * Fr::N, local_n(3, s->N), 0, &sh->msm_h));
+    ZKB_TRY(g1->msm_run(ctx, side[3], pk->l, 0, zr + (s->n_inputs - 1 + pk->pair_lo[4]) * Fr::N, local_n(4, s->n_aux), 0,
+                        &sh->msm_l));
+    for (int i : {1, 3, 5}) {
+      ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
+      ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));
+    }
+    ZKB_LAUNCH(ctx, (k_g16_local_c<Fq, Fq2>), 1, 32, 0, st, sh);
+    return ZKB_OK;
+  }
+
+  static int fetch_partial(zkb_ctx* ctx, void* out) {
+    Groth16Stage* s = ctx->stage;
+    if (!s || !s->shard) return set_err(ctx, ZKB_E_INVALID, "groth16: no partial computed");
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out, &((Shard*)s->shard)->part, sizeof(Part), cudaMemcpyDeviceToHost, ctx->main));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(ctx->main));
+    return ZKB_OK;
+  }
+
+  // partials == nullptr: all-gather this rank's stage->shard->part over the communicator (the product path);
+  // otherwise `count` partials from the host (transport supplied by the caller; the single-GPU tests).
+  // recompute_fixed: run the r / s dependent kernels again (a fold that did not follow prove_partial_staged on this ctx).
+  static int fold_partials(zkb_ctx* ctx, const zkb_pk* pk, const void* partials, size_t count, const uint64_t* r,
+                           const uint64_t* sc, bool recompute_fixed) {
+    Groth16Stage* s = ctx->stage;
+    if (!pk || pk->curve != CURVE || pk->ctx != ctx || !pk->sharded)
+      return set_err(ctx, ZKB_E_INVALID, "groth16: not a sharded proving key of this context");
+    if (!s) { ctx->stage = new Groth16Stage(); s = ctx->stage; }
+    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, sizeof(Res)));
+    if (!s->scal) ZKB_CUDA(ctx, cudaMalloc(&s->scal, sizeof(Fr) * 4));
+    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, sizeof(Shard)));
+    cudaStream_t st = ctx->main;
+    Res* res = (Res*)s->results;
+    Shard* sh = (Shard*)s->shard;
+    if (recompute_fixed) {
+      if (!r || !sc) return set_err(ctx, ZKB_E_INVALID, "groth16: null r/s");
+      Fr r_val, s_val;
+      memcpy(r_val.v, r, 32);
+      memcpy(s_val.v, sc, 32);
+      ZKB_LAUNCH(ctx, (k_g16_scalars<FrP, Fq, Fq2>), 4, 32, 0, st, r_val, s_val, (Fr*)s->scal, (const Affine<Fq>*)pk->g1_singles,
+                 (const Affine<Fq2>*)pk->g2_singles, res);
+      ZKB_LAUNCH(ctx, (k_g16_fixed<FrP, Fq, Fq2>), 3, 32, 0, st, (const Fr*)s->scal, (const Affine<Fq>*)pk->q0_g1,
+                 (const Affine<Fq2>*)pk->q0_g2, (const Affine<Fq>*)pk->g1_singles, (const Affine<Fq2>*)pk->g2_singles,
+                 (const Res*)res, sh);
+    }
+    void* d_all;
+    if (partials) {
+      ZKB_TRY(comm_gather_buffer(ctx, sizeof(Part) * count, &d_all));
+      ZKB_CUDA(ctx, cudaMemcpyAsync(d_all, partials, sizeof(Part) * count, cudaMemcpyDefault, st));
+    } else {
+      count = (size_t)ctx->n_ranks;
+      if (pk->n_ranks != ctx->n_ranks || pk->rank != ctx->rank)
+        return set_err(ctx, ZKB_E_INVALID, "groth16: key sharded for rank %d of %d, communicator is rank %d of %d", pk->rank,
+                       pk->n_ranks, ctx->rank, ctx->n_ranks);
+      ZKB_TRY(comm_gather_buffer(ctx, sizeof(Part) * count, &d_all));
+      ZKB_TRY(comm_allgather(ctx, st, &sh->part, d_all, sizeof(Part)));
+    }
+    ZKB_LAUNCH(ctx, (k_g16_fold_finish<Fq, Fq2>), 3, 32, 0, st, (const Part*)d_all, (uint32_t)count, (const Shard*)sh, res);
+    return ZKB_OK;
+  }
+
   static const Groth16Ops* ops() {
     static const Groth16Ops o = {&stage, &compute_h, &prove_staged, &fetch_proof, &fetch_h,
-                                 sizeof(Affine<Fq>), sizeof(Affine<Fq2>)};
+                                 sizeof(Affine<Fq>), sizeof(Affine<Fq2>),
+                                 &prove_partial_staged, &fetch_partial, &fold_partials, sizeof(Part)};
     return &o;
   }
 };

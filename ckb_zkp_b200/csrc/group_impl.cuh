@@ -34,9 +34,16 @@ struct GroupImpl {
                (uint32_t)n, (Affine<F>*)d_out, d_inf);
     return ZKB_OK;
   }
+  static int fold(zkb_ctx* ctx, cudaStream_t st, const void* d_points, uint32_t count, uint32_t stride_bytes, void* d_out_pt,
+                  void* d_out_affine, uint8_t* d_out_inf) {
+    if (count == 0) return set_err(ctx, ZKB_E_INVALID, "fold: no points");
+    ZKB_LAUNCH(ctx, (k_fold_points<F>), 1, 32, 0, st, (const XYZZ<F>*)d_points, count, stride_bytes, (XYZZ<F>*)d_out_pt,
+               (Affine<F>*)d_out_affine, d_out_inf);
+    return ZKB_OK;
+  }
   static const GroupOps* ops() {
     static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host,
-                               &fixed_base_mul};
+                               &fixed_base_mul, &fold};
     return &o;
   }
 };

@@ -31,6 +31,9 @@ struct zkb_srs {
   int precomp;       // table holds W * n points (window-major) when set
   void* table;       // Affine<F>[(precomp ? W : 1) * n]
   uint8_t* inf;      // n flags
+  // multi-GPU: this SRS holds bases [global_lo, global_lo + n) of a logical SRS of global_n bases
+  // (zkb_srs_upload_shard); an unsharded SRS has global_lo = 0, global_n = n
+  size_t global_lo, global_n;
 };
 
 namespace zkb {
@@ -477,6 +480,27 @@ __global__ void k_to_affine(const XYZZ<F>* __restrict__ in, uint32_t n, Affine<F
   out_inf[i] = p.is_inf() ? 1 : 0;
 }
 
+// sum of `count` points in index order (= rank order of the all-gather of per-rank partials) -> out_pt and/or
+// canonical affine.  One thread: count <= 8 ranks, ~14 multiplications per addition.
+template <class F>
+__global__ void k_fold_points(const XYZZ<F>* __restrict__ in, uint32_t count, uint32_t stride_bytes,
+                              XYZZ<F>* __restrict__ out_pt, Affine<F>* __restrict__ out_xy, uint8_t* __restrict__ out_inf) {
+  if (threadIdx.x | blockIdx.x) return;
+  const char* base = reinterpret_cast<const char*>(in);
+  XYZZ<F> acc = ld_vec_rw(reinterpret_cast<const XYZZ<F>*>(base));
+  for (uint32_t i = 1; i < count; i++) {
+    XYZZ<F> q = ld_vec_rw(reinterpret_cast<const XYZZ<F>*>(base + (size_t)i * stride_bytes));
+    pt_add(acc, q);
+  }
+  if (out_pt) st_vec(out_pt, acc);
+  if (out_xy) {
+    Affine<F> a;
+    pt_to_affine(a, acc);
+    st_vec(out_xy, a);
+    *out_inf = acc.is_inf() ? 1 : 0;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // SRS ingestion: apply infinity flags, precompute 2^(c*j) * P_i
 // ------------------------------------------------------------------------------------------
@@ -545,12 +569,23 @@ inline int msm_pair_levels(size_t max_entries, uint32_t n_buckets) {
   return 0;
 }
 
+// resident blocks per SM of a level kernel.  The dynamic shared-memory opt-in is a per-DEVICE function attribute, so it
+// is set on every call (a process may hold contexts on several GPUs); the occupancy answer is the same on all of them.
 inline int pair_level_occupancy(const void* kernel, size_t smem_bytes) {
   int blocks = 0;
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, kPairThreads, smem_bytes) != cudaSuccess || blocks < 1)
     blocks = 1;
   return blocks;
+}
+// slots per thread and chunk = scale * (5 .. 11): large enough to amortise the block's inversion and tree, small
+// enough for >= ~6 chunks per resident block
+inline uint32_t pair_level_scale(size_t slots_bound, unsigned resident_blocks) {
+  const char* e = getenv("ZKB_PAIR_SCALE");             // read per call: the tuning script sweeps it
+  const int forced = e ? atoi(e) : 0;
+  if (forced >= 1 && forced <= 16) return (uint32_t)forced;
+  size_t per_block = slots_bound / ((size_t)resident_blocks * kPairThreads * 8 * 6 + 1);
+  return per_block < 1 ? 1u : per_block > 4 ? 4u : (uint32_t)per_block;
 }
 
 template <class F, class FrP>
@@ -647,7 +682,7 @@ struct MsmEngine {
     if (levels > 0) {
       auto halved = [&](size_t e) { return (e + (e < n_buckets ? e : (size_t)n_buckets) + 1) / 2; };
       const size_t e1 = halved(max_entries), e2 = halved(e1);
-      uint32_t *off_a, *off_b;
+      uint32_t *off_a, *off_b, *work_counters;
       uint2* recs;
       F* prefix;
       Aff *pts_a, *pts_b;
@@ -657,6 +692,8 @@ struct MsmEngine {
       ZKB_TRY(ws.alloc(&prefix, e1));
       ZKB_TRY(ws.alloc(&pts_a, e1));
       ZKB_TRY(ws.alloc(&pts_b, levels > 1 ? e2 : 1));
+      ZKB_TRY(ws.alloc(&work_counters, (size_t)levels));
+      ZKB_CUDA(ctx, cudaMemsetAsync(work_counters, 0, sizeof(uint32_t) * (size_t)levels, st));
       const uint32_t* off_in = offsets;
       size_t e_out = e1;
       for (int lvl = 0; lvl < levels; lvl++) {
@@ -669,11 +706,13 @@ struct MsmEngine {
                    (uint32_t*)nullptr);
         // one resident wave; the kernel derives the slots per thread from the list length on the device
         ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
-          static const int occ = pair_level_occupancy((const void*)k_pair_level<F>, PairRing<F>::kBytes);
+          const int occ = pair_level_occupancy((const void*)k_pair_level<F>, PairRing<F>::kBytes);
+          const unsigned blocks = (unsigned)(ctx->sm_count * occ);
           prof_begin(ctx, bs);
-          ZKB_LAUNCH(ctx, (k_pair_level<F>), (unsigned)(ctx->sm_count * occ), kPairThreads, PairRing<F>::kBytes, bs,
+          ZKB_LAUNCH(ctx, (k_pair_level<F>), blocks, kPairThreads, PairRing<F>::kBytes, bs,
                      lvl == 0 ? (const uint32_t*)entries : (const uint32_t*)nullptr, lvl == 0 ? (const Aff*)srs->table : acc_pts,
-                     off_in, (const uint32_t*)off_out, n_buckets, recs, prefix, pts_out);
+                     off_in, (const uint32_t*)off_out, n_buckets, recs, prefix, pts_out, work_counters + lvl,
+                     pair_level_scale(e_out, blocks));
           prof_end(ctx, bs, 0.0);
           return ZKB_OK;
         }));
@@ -845,6 +884,10 @@ struct GroupOps {
   // out = k * P for `count` (scalar, point) pairs, one thread each (small counts: proof assembly)
   int (*fixed_base_mul)(zkb_ctx*, cudaStream_t, const void* d_base_affine, const uint32_t* d_scalars, size_t n,
                         void* d_out_affine, uint8_t* d_out_inf);
+  // sum of `count` XYZZ points laid out `stride_bytes` apart (rank order) -> d_out_pt (XYZZ, may be null) and/or
+  // canonical affine d_out_affine + d_out_inf (may be null)
+  int (*fold)(zkb_ctx*, cudaStream_t, const void* d_points, uint32_t count, uint32_t stride_bytes, void* d_out_pt,
+              void* d_out_affine, uint8_t* d_out_inf);
 };
 const GroupOps* group_ops(int curve, int group);
 

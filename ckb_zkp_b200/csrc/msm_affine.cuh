@@ -22,6 +22,14 @@
 // are copied into a per-thread shared-memory ring with cp.async while the current slot multiplies
 // (no registers held, no scoreboard stall: the gathers of level 0 are ~1 us away).
 //
+// Work distribution (round 2): the slots of a level are cut into chunks of 128 * m_j slots whose lengths m_j cycle
+// through a fixed pattern of DIFFERENT values, and the resident blocks draw chunks from an atomic counter.  Blocks of
+// equal length started together reach their (single-thread, ~150 k cycle) inversion at the same moment and leave the
+// multiplier pipe idle for a third of the time -- measured 41-61 % pipe utilisation in round 1 with equal passes on
+// one resident wave; unequal chunks drift out of phase at once, so while one block of an SM inverts the others multiply.
+// Dynamic chunks also make the kernel indifferent to how many of its blocks are resident when several MSMs share the
+// machine (the five MSMs of a proof run on five streams).
+//
 // A level is: k_pair_sizes -> exclusive scan (msm.cuh) -> k_pair_level.
 // Identity = affine (0, 0), as everywhere on the device; P + (-P), doublings and identities are
 // handled (they do not occur for honest inputs, but bases are not required to be distinct).
@@ -36,6 +44,19 @@ constexpr int kPairThreads = 128;             // threads per block = leaves of t
 constexpr uint32_t kPairMinM = 4;             // output slots per thread and pass: lower / upper limit
 constexpr uint32_t kPairMaxM = 128;
 constexpr uint32_t kPairNone = 0xffffffffu;   // second source of a slot that only carries one point over
+// chunk j of a level holds 128 * scale * kPairUnits[j % 8] slots (64 units per period of 8 chunks)
+constexpr int kPairPeriod = 8;
+constexpr uint32_t kPairPeriodUnits = 64;
+__host__ __device__ __forceinline__ uint32_t pair_chunk_units(uint32_t j) {
+  // 5, 11, 7, 9, 6, 10, 8, 8 packed in nibbles (lowest nibble = j % 8 == 0)
+  return (0x88A6975Bu >> (4 * (j % kPairPeriod))) & 0xFu;
+}
+__host__ __device__ __forceinline__ uint32_t pair_chunk_start_units(uint32_t j) {
+  // exclusive prefix sums of the pattern: 0, 5, 16, 23, 32, 38, 48, 56
+  const uint32_t k = j % kPairPeriod;
+  const uint32_t pre = k == 0 ? 0u : k == 1 ? 5u : k == 2 ? 16u : k == 3 ? 23u : k == 4 ? 32u : k == 5 ? 38u : k == 6 ? 48u : 56u;
+  return (j / kPairPeriod) * kPairPeriodUnits + pre;
+}
 
 // cnt_out[b] = ceil(k_b / 2)
 static __global__ void k_pair_sizes(const uint32_t* __restrict__ off_in, uint32_t nb, uint32_t* __restrict__ cnt_out) {
@@ -123,32 +144,31 @@ __device__ __forceinline__ bool pair_denominator(const Affine<F>* pts, uint2 rec
 
 // One level.  entries != nullptr (level 0): the input lists are the sorted (negate | table index) entries and
 // pts is the base table; else the lists are the previous level's dense points.  off_in / off_out: bucket
-// offsets of the input / output lists (nb + 1 each).  The grid is one resident wave; a block takes
-// 128 * M slots per pass with M = ceil(E / threads) derived on the device (E is only known there), in
-// several equal passes when that exceeds kPairMaxM.
+// offsets of the input / output lists (nb + 1 each).  The grid is (at most) one resident wave of blocks that draw
+// chunks of 128 * M slots (M = scale * pattern[j % 8]) from *work_counter (zeroed by the host) until the E output
+// slots of the level are used up.
 template <class F>
 __global__ void __launch_bounds__(kPairThreads, sizeof(F) <= 48 ? 3 : 2)
 k_pair_level(const uint32_t* __restrict__ entries, const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ off_in,
              const uint32_t* __restrict__ off_out, uint32_t nb, uint2* __restrict__ recs, F* __restrict__ prefix,
-             Affine<F>* __restrict__ out) {
+             Affine<F>* __restrict__ out, uint32_t* __restrict__ work_counter, uint32_t scale) {
   using Ring = PairRing<F>;
   // dynamic shared memory (PairRing<F>::kBytes): the operand ring; between the forward and the backward phase,
   // while the ring is idle, its first bytes hold the inversion tree (node i: children 2i, 2i + 1; leaves at
   // kPairThreads + tid)
   extern __shared__ uint4 pair_smem[];
+  __shared__ uint32_t chunk_sh;
   F* tree = reinterpret_cast<F*>(pair_smem);
   const uint32_t tid = threadIdx.x;
   Ring ring{pair_smem + tid};
   const uint32_t E = off_out[nb];
-  const uint32_t T = gridDim.x * kPairThreads;
-  uint32_t M = (E + T - 1) / T;
-  if (M > kPairMaxM) {                            // several passes of equal length
-    const uint32_t passes = (M + kPairMaxM - 1) / kPairMaxM;
-    M = (M + passes - 1) / passes;
-  }
-  if (M < kPairMinM) M = kPairMinM;
-  const uint64_t per_pass = (uint64_t)T * M;
-  for (uint64_t base64 = (uint64_t)blockIdx.x * kPairThreads * M; base64 < E; base64 += per_pass) {   // block-uniform
+  for (;;) {                                      // block-uniform
+    if (tid == 0) chunk_sh = atomicAdd(work_counter, 1u);
+    __syncthreads();
+    const uint32_t chunk = chunk_sh;
+    const uint64_t base64 = (uint64_t)kPairThreads * scale * pair_chunk_start_units(chunk);
+    if (base64 >= E) break;
+    const uint32_t M = scale * pair_chunk_units(chunk);
     const uint32_t base = (uint32_t)base64;
     const uint32_t range_end = E - base < kPairThreads * M ? E : base + kPairThreads * M;
 
@@ -280,7 +300,7 @@ k_pair_level(const uint32_t* __restrict__ entries, const Affine<F>* __restrict__
       }
       cp_async_wait<0>();
     }
-    __syncthreads();                              // tree, ring and records are reused by the next pass
+    __syncthreads();                              // tree, ring, records and chunk_sh are reused by the next chunk
   }
 }
 

@@ -5,8 +5,19 @@
 
 namespace zkb {
 
-constexpr unsigned kTileLog = 10;          // elements per shared-memory tile = 1024
-constexpr unsigned kMinRunLog = 2;         // later passes read >= 4 contiguous elements (128 B)
+// Tile geometry (runtime switches, read once): 2^tile_log elements per shared-memory tile (32 bytes each: 2^10 = 32 KiB,
+// 2^11 = 64 KiB of the 227 KiB an SM offers), later passes read runs of 2^min_run_log contiguous elements.
+// 2^11-element tiles with 64-byte runs turn a 2^21 transform into 11 + 10 stages = TWO passes over HBM instead of three.
+struct NttGeom { unsigned tile_log, min_run_log; };
+static NttGeom ntt_geom() {
+  static const NttGeom g = []() {
+    NttGeom r{11u, 1u};
+    if (const char* e = getenv("ZKB_NTT_TILE")) { int v = atoi(e); if (v >= 8 && v <= 12) r.tile_log = (unsigned)v; }
+    if (const char* e = getenv("ZKB_NTT_RUN")) { int v = atoi(e); if (v >= 0 && v <= 4) r.min_run_log = (unsigned)v; }
+    return r;
+  }();
+  return g;
+}
 
 template <class FrP>
 __global__ void k_domain_consts(unsigned log_n, Fp<FrP>* c) {
@@ -163,6 +174,7 @@ static int ntt_run_t(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data
   if (log_n == 0) return ZKB_OK;      // size-1 transform is the identity (g^0 = 1, 1/1 = 1)
 
   // plan the passes
+  const unsigned kTileLog = ntt_geom().tile_log, kMinRunLog = ntt_geom().min_run_log;
   unsigned ks[8], np = 0;
   unsigned k1 = log_n < kTileLog ? log_n : kTileLog;
   ks[np++] = k1;
@@ -182,7 +194,11 @@ static int ntt_run_t(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data
     static const unsigned div = []() { const char* e = getenv("ZKB_NTT_DIV"); unsigned v = e ? (unsigned)atoi(e) : 4u; return v < 2 ? 2u : v; }();
     unsigned threads = E / div < 32 ? 32 : E / div;      // div / 2 butterflies per thread and stage; measured at 2^21: 0.578 / 0.520 / 0.538 ms for div = 2 / 4 / 8
     size_t tiles = dom->n >> (k + t);
-    ZKB_LAUNCH(ctx, (k_ntt_pass<FrP>), (unsigned)tiles, threads, sizeof(uint32_t) * Fr::N * E, st, src, dst, tw, log_n, s0, k,
+    if (threads > 512) threads = 512;                    // __launch_bounds__ of the pass kernel; the loops stride by blockDim
+    const size_t smem = sizeof(uint32_t) * Fr::N * E;
+    if (smem > 48 * 1024)                                // opt-in above 48 KiB is a per-device function attribute: set per call
+      ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_ntt_pass<FrP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ZKB_LAUNCH(ctx, (k_ntt_pass<FrP>), (unsigned)tiles, threads, smem, st, src, dst, tw, log_n, s0, k,
                t, p == 0 ? 1 : 0, p == 0 ? pre : (const Fr*)nullptr, p == np - 1 ? post : (const Fr*)nullptr,
                p == np - 1 ? pconst : (const Fr*)nullptr);
     s0 += k;

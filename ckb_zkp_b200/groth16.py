@@ -37,13 +37,16 @@ class Parameters:
     Point arrays are (xy uint64[n, words], inf uint8[n]) pairs in the layout of include/zkb.h."""
 
     def __init__(self, ctx, curve, a_query, b_g1_query, b_g2_query, h_query, l_query, alpha_g1, beta_g1, delta_g1,
-                 beta_g2, delta_g2):
-        self.ctx, self.curve = ctx, curve
+                 beta_g2, delta_g2, shard=None):
+        """shard = (n_ranks, rank): one process per GPU, every rank passes the whole key and keeps only its slice of
+        the pairs of each MSM resident; every rank then calls create_proof with the same arguments (collective) and
+        gets the same proof (zkb_groth16_prove_sharded)."""
+        self.ctx, self.curve, self.shard = ctx, curve, shard
         self.n_a, self.n_h, self.n_l = len(a_query[1]), len(h_query[1]), len(l_query[1])
         g1s = np.stack([np.asarray(x, dtype=np.uint64).reshape(point_words(curve, _lib.G1))
                         for x in (alpha_g1, beta_g1, delta_g1)])
         g2s = np.stack([np.asarray(x, dtype=np.uint64).reshape(point_words(curve, _lib.G2)) for x in (beta_g2, delta_g2)])
-        self.pk = ctx.groth16_pk(curve, a_query, b_g1_query, b_g2_query, h_query, l_query, g1s, g2s)
+        self.pk = ctx.groth16_pk(curve, a_query, b_g1_query, b_g2_query, h_query, l_query, g1s, g2s, shard=shard)
 
     def free(self):
         self.pk.free()
@@ -74,8 +77,8 @@ def prove_assignment(params, prover, r, s):
         z_mont = ctx.fr_convert(curve, ints_to_limbs(prover.input_assignment + prover.aux_assignment), to_mont=True)
     from .backend import ZkbError
     try:
-        a, b, c = ctx.groth16_prove(params.pk, A, B, C, z_mont, n_inputs, n_aux, ints_to_limbs([r % p])[0],
-                                    ints_to_limbs([s % p])[0])
+        prove = ctx.groth16_prove_sharded if getattr(params, "shard", None) else ctx.groth16_prove
+        a, b, c = prove(params.pk, A, B, C, z_mont, n_inputs, n_aux, ints_to_limbs([r % p])[0], ints_to_limbs([s % p])[0])
     except ZkbError as e:
         if e.code == _lib.E_TOO_LARGE:          # EvaluationDomain::new -> None (r1cs_to_qap.rs:123-125)
             raise PolynomialDegreeTooLarge() from e

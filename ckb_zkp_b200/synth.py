@@ -81,6 +81,7 @@ class MimcInstance:
         vals = stream_field_ints(seed, 0, rounds + 2, p)
         xl, xr, consts = vals[0], vals[1], vals[2:]
         self.curve, self.n_constraints, self.p = curve, n_constraints, p
+        self.seed, self.consts = seed, consts          # the matrices below carry THESE round constants
         self.n_inputs, self.n_aux = 2, n_constraints + 1
         # variable numbering (global column index): 0 = ONE, 1 = image (last xl'), aux k -> 2 + k
         # aux 0 = xl0, aux 1 = xr0, round i: tmp_i = aux 2+2i, xl'_i = aux 3+2i (except the last: input 1)
@@ -129,7 +130,7 @@ class MimcInstance:
     def coeff_ints(self, which):
         """canonical coefficient list of matrix `which` (small instances / tests)"""
         row_ptr, cols, codes, per = getattr(self, which)
-        consts = stream_field_ints(MIMC_SEED, 2, self.n_constraints // 2, self.p)
+        consts = self.consts
         out = []
         for idx, code in enumerate(codes):
             out.append(1 if code == 1 else self.p - 1 if code == -2 else consts[idx // per])
@@ -140,7 +141,7 @@ class MimcInstance:
         from .backend import CsrMatrix
         p = self.p
         rounds = self.n_constraints // 2
-        consts = stream_field_ints(MIMC_SEED, 2, rounds, p)
+        consts = self.consts
         table = ctx.fr_convert(self.curve, ints_to_limbs(consts + [1, p - 1]), to_mont=True)
         mats = []
         for which in "ABC":
@@ -181,8 +182,10 @@ class SyntheticKey:
         self.l = random_exponents(rng, n_vars - n_inputs)
         self.alpha, self.beta, self.delta = [random_exponents(rng, 1)[0] for _ in range(3)]
 
-    def upload(self, ctx, curve, chunk=1 << 18):
-        """points = exponent * generator, computed on the GPU (zkb_fixed_base_mul) -> groth16.Parameters"""
+    def upload(self, ctx, curve, chunk=1 << 18, shard=None, keep_host=False):
+        """points = exponent * generator, computed on the GPU (zkb_fixed_base_mul) -> groth16.Parameters.
+        shard = (n_ranks, rank): a key sharded over the ranks (every rank computes the whole key, keeps its slice).
+        keep_host: also keep the point arrays on the host as self.host_points (the CPU baseline proves with them)."""
         from .groth16 import Parameters
 
         def pts(group, k):
@@ -196,9 +199,12 @@ class SyntheticKey:
 
         singles1, _ = pts(_lib.G1, np.stack([self.alpha, self.beta, self.delta]))
         singles2, _ = pts(_lib.G2, np.stack([self.beta, self.delta]))
-        return Parameters(ctx, curve, pts(_lib.G1, self.a), pts(_lib.G1, self.b), pts(_lib.G2, self.b),
-                          pts(_lib.G1, self.h), pts(_lib.G1, self.l), singles1[0], singles1[1], singles1[2],
-                          singles2[0], singles2[1])
+        q = {"a": pts(_lib.G1, self.a), "b1": pts(_lib.G1, self.b), "b2": pts(_lib.G2, self.b), "h": pts(_lib.G1, self.h),
+             "l": pts(_lib.G1, self.l)}
+        if keep_host:
+            self.host_points = dict(q, g1_singles=singles1, g2_singles=singles2)
+        return Parameters(ctx, curve, q["a"], q["b1"], q["b2"], q["h"], q["l"], singles1[0], singles1[1], singles1[2],
+                          singles2[0], singles2[1], shard=shard)
 
     def expected_exponents(self, p, z, h, r, s):
         """(A, B, C) exponents of the proof for assignment z (ints, z[0] = 1), h (ints), r, s --

@@ -151,6 +151,73 @@ int zkb_groth16_prove_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t r_ca
                              const uint64_t s_canonical[4]);
 int zkb_groth16_fetch_proof(zkb_ctx* ctx, const zkb_pk* pk, uint64_t* proof_xy, uint8_t* proof_inf);
 
+/* ---- multi-GPU: one process (one ctx) per GPU, NCCL over NVLink / NVSwitch ---------------------------
+ * The reference runs in one address space (rayon, groth16/Cargo.toml:14); what shards here is what is independent
+ * there: the pairs of every MSM (a plain sum, curve/src/lib.rs:38-45; the five Groth16 MSMs share only read-only
+ * inputs, groth16/src/prover.rs:164-190; Marlin commits polynomial by polynomial, marlin/src/pc/mod.rs:42-69).
+ * Each rank keeps a contiguous slice of the bases resident, computes its partial sum, and the ranks exchange ONE
+ * all-gather of fixed-size partial points (NCCL has no EC-add reduction) which every rank folds in rank order:
+ * all ranks return the identical canonical affine result.
+ * Rendezvous: rank 0 calls zkb_comm_unique_id, the host distributes the 128 bytes by its own means
+ * (torch.distributed / MPI / a file), every rank calls zkb_comm_init (collective).  NCCL is dlopen'ed
+ * (libnccl.so.2); single-GPU users never need it. */
+#define ZKB_COMM_ID_BYTES 128
+int zkb_comm_unique_id(zkb_ctx* ctx, uint8_t id[ZKB_COMM_ID_BYTES]);
+int zkb_comm_init(zkb_ctx* ctx, int n_ranks, int rank, const uint8_t id[ZKB_COMM_ID_BYTES]);
+void zkb_comm_destroy(zkb_ctx* ctx);
+int zkb_comm_rank(zkb_ctx* ctx);
+int zkb_comm_size(zkb_ctx* ctx);
+/* all-gathers this ctx has enqueued so far (bench.py reports it next to gpu_launches) */
+uint64_t zkb_comm_collectives(zkb_ctx* ctx);
+
+/* This rank's slice [global_lo, global_lo + n_local) of a logical SRS of global_n bases. */
+int zkb_srs_upload_shard(zkb_ctx* ctx, int curve, int group, const uint64_t* xy_mont_local, const uint8_t* inf_local,
+                         size_t n_local, size_t global_lo, size_t global_n, unsigned flags, zkb_srs** out);
+/* VariableBaseMSM::multi_scalar_mul(&bases[base_offset..], &scalars[..n]) over the LOGICAL SRS, every rank passing the
+ * same full-length scalar array (host or device; only the local slice is read) -- the call shape of the reference,
+ * where every rank holds the same polynomial / assignment.  Collective: local partial, one all-gather, fold. */
+int zkb_msm_sharded(zkb_ctx* ctx, const zkb_srs* srs_shard, size_t base_offset, const uint64_t* scalars, size_t n,
+                    int scalars_mont, uint64_t* out_xy, uint8_t* out_inf);
+/* Same exchange for a stand-alone MSM whose scalars are sharded like the bases: d_scalars_local (device, canonical)
+ * pairs with the first n_local bases of the shard (BASELINE configs[2]). */
+int zkb_msm_sharded_local(zkb_ctx* ctx, const zkb_srs* srs_shard, const void* d_scalars_local, size_t n_local,
+                          uint64_t* out_xy, uint8_t* out_inf);
+/* The two halves of zkb_msm_sharded for a host that brings its own transport: the rank's partial point
+ * (zkb_partial_bytes(curve, group) bytes, XYZZ coordinates), and the fold of `count` partials in index order. */
+size_t zkb_partial_bytes(int curve, int group);
+int zkb_msm_partial(zkb_ctx* ctx, const zkb_srs* srs_shard, size_t base_offset, const uint64_t* scalars, size_t n,
+                    int scalars_mont, void* partial_out);
+int zkb_msm_fold(zkb_ctx* ctx, int curve, int group, const void* partials, size_t count, uint64_t* out_xy, uint8_t* out_inf);
+
+/* Parameters<E> sharded over the ranks: the caller passes the WHOLE queries (every rank deserialises the same key
+ * file) and the library keeps only this rank's slice of the pairs of each of the five MSMs resident. */
+int zkb_groth16_pk_create_sharded(zkb_ctx* ctx, int curve,
+                                  const uint64_t* a_query, const uint8_t* a_inf, size_t a_len,
+                                  const uint64_t* b_g1_query, const uint8_t* b_g1_inf, size_t b_g1_len,
+                                  const uint64_t* b_g2_query, const uint8_t* b_g2_inf, size_t b_g2_len,
+                                  const uint64_t* h_query, const uint8_t* h_inf, size_t h_len,
+                                  const uint64_t* l_query, const uint8_t* l_inf, size_t l_len,
+                                  const uint64_t* g1_singles, const uint64_t* g2_singles, int n_ranks, int rank,
+                                  zkb_pk** out);
+/* ONE proof computed by all ranks together (strong scaling; same arguments and result as zkb_groth16_prove on every
+ * rank): witness_map on every rank, the five MSMs over the rank's pairs, s * A_k + r * B1_k + L_k + H_k formed
+ * locally, one all-gather of (A_k, C_k, B2_k), fold + into_affine. */
+int zkb_groth16_prove_sharded(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                              const uint64_t* z_mont, size_t n_inputs, size_t n_aux,
+                              const uint64_t r_canonical[4], const uint64_t s_canonical[4],
+                              uint64_t* proof_xy, uint8_t* proof_inf);
+/* after zkb_groth16_stage: the device path alone (result fetched with zkb_groth16_fetch_proof) */
+int zkb_groth16_prove_sharded_staged(zkb_ctx* ctx, const zkb_pk* pk, const uint64_t r_canonical[4],
+                                     const uint64_t s_canonical[4]);
+/* The two halves for a host with its own transport: the rank's partial (zkb_groth16_partial_bytes(curve) bytes)
+ * and the fold of `count` partials in rank order into the proof. */
+size_t zkb_groth16_partial_bytes(int curve);
+int zkb_groth16_prove_partial(zkb_ctx* ctx, const zkb_pk* pk, const zkb_csr* A, const zkb_csr* B, const zkb_csr* C,
+                              const uint64_t* z_mont, size_t n_inputs, size_t n_aux,
+                              const uint64_t r_canonical[4], const uint64_t s_canonical[4], void* partial_out);
+int zkb_groth16_fold(zkb_ctx* ctx, const zkb_pk* pk, const void* partials, size_t count,
+                     const uint64_t r_canonical[4], const uint64_t s_canonical[4], uint64_t* proof_xy, uint8_t* proof_inf);
+
 /* ---- fixed-base batch multiplication (setup side; groth16/src/generator.rs:205-256) -------
  * out[i] = scalars[i] * G for one affine base point G; result-identical to ark FixedBaseMSM
  * followed by batch_normalization.  Used to mint synthetic SRS on the device. */

@@ -10,6 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "c", "libzkref.so")
+LIB_V3 = os.path.join(HERE, "c", "libzkref_v3.so")     # -march=x86-64-v3 build of the same source
 SRC = os.path.join(HERE, "c", "zkref.cpp")
 
 c_void_p, c_int, c_uint, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_size_t
@@ -33,16 +34,38 @@ def build(force=False):
 
 
 _lib = None
+_variant = None
+
+
+def _host_is_v3():
+    """x86-64-v3 needs (among others) bmi2 (mulx), avx2, fma, movbe; adx is what arkworks' `asm` feature also asks for"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    return {"bmi1", "bmi2", "avx2", "fma", "movbe", "adx", "abm"} <= flags
+    except OSError:
+        pass
+    return False
 
 
 def lib():
-    global _lib
+    global _lib, _variant
     if _lib is None:
         if not os.path.exists(LIB):
             build()
-        _lib = ctypes.CDLL(LIB)
+        use_v3 = os.environ.get("ZKREF_GENERIC") != "1" and os.path.exists(LIB_V3) and _host_is_v3()
+        _lib = ctypes.CDLL(LIB_V3 if use_v3 else LIB)
+        _variant = "x86-64-v3 (mulx/adx/avx2)" if use_v3 else "generic x86-64"
         _lib.zkref_threads.restype = c_int
     return _lib
+
+
+def variant():
+    """which build of zkref.cpp is loaded (stated next to every CPU baseline number)"""
+    lib()
+    return _variant
 
 
 def threads():

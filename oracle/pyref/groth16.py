@@ -164,3 +164,17 @@ def proof_in_exponent(pk, cs, r, s, h=None):
         C = (C - r * B) % p
     c1, c2 = G1(cid), G2(cid)
     return c1.mul_affine(d["g1"], A), c2.mul_affine(d["g2"], B), c1.mul_affine(d["g1"], C)
+
+
+def verifying_key(pk):
+    """VerifyKey<E> of the parameters (groth16/src/lib.rs:59-66) in the form pairing.prepare_verifying_key takes"""
+    return {"alpha_g1": pk.alpha_g1, "beta_g2": pk.beta_g2, "gamma_g2": pk.gamma_g2, "delta_g2": pk.delta_g2,
+            "gamma_abc_g1": pk.gamma_abc_g1}
+
+
+def verify_proof(pk, proof, public_inputs):
+    """prepare_verifying_key + verify_proof (verifier.rs:8-44) -- the reference's own acceptance test
+    (groth16/tests/mini.rs:85-89).  public_inputs excludes ONE, like the reference's `&[Fr]` argument."""
+    from . import pairing
+    pvk = pairing.prepare_verifying_key(pk.curve_id, verifying_key(pk))
+    return pairing.verify_proof(pk.curve_id, pvk, proof, public_inputs)

@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-sample-log", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--log-constraints", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -20,7 +20,10 @@ def test_reference_arm_prints_one_json_line():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
         assert key in line, key
     assert line["impl"] == "reference" and line["unit"] == "proofs/s" and line["higher_is_better"] is True
-    assert line["metric"] == "groth16_proofs_per_sec_bls12_381_2e20_constraints"
+    assert line["metric"] == "groth16_proofs_per_sec_bls12_381_2e8_constraints"
+    assert line["steps"] == 2 and line["warmup"] == 1
+    # every step is a full proof at the requested size: no sample-and-scale
+    assert "2^8" in line["config"]["workload"] and "no scaling" in line["cpu_baseline"]["sample"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0

@@ -118,6 +118,27 @@ def test_reference_api_mini(ctx):
     params.free()
 
 
+@pytest.mark.parametrize("name,cid", [("groth16_mini_bls12_381", BLS12_381), ("groth16_mini_bn254", BN254)])
+def test_gpu_proofs_pass_the_reference_acceptance_test(ctx, name, cid):
+    """groth16/tests/mini.rs:46-97 end to end with the GPU prover in the middle: parameters from the (restated) generator,
+    `create_random_proof` on the GPU, then the reference's own acceptance test -- prepare_verifying_key + verify_proof
+    (groth16/src/verifier.rs:8-44, pairing restated in oracle/pyref/pairing.py) -- on the GPU's proof points."""
+    g = load(name)
+    params = params_from_golden(ctx, g)
+    fr = FR[cid]
+    cs = mini_circuit(ConstraintSystem(fr.p))
+    alpha, beta, gamma, delta, t = [stream_field(1, i, fr.p) for i in range(5)]
+    pk = OG.generate_parameters(cs, cid, alpha, beta, gamma, delta, t)
+    to_points = lambda proof: tuple(H.array_point(cid, grp, xy, inf) for grp, (xy, inf) in zip((1, 2, 1), (proof.a, proof.b, proof.c)))
+    proof = zg.create_random_proof(params, MiniCircuit(2, 3, 10, 10), random.Random(2024))
+    assert OG.verify_proof(pk, to_points(proof), [10])
+    assert not OG.verify_proof(pk, to_points(proof), [11])
+    assert OG.verify_proof(pk, to_points(zg.create_proof_no_zk(params, MiniCircuit(2, 3, 10, 10))), [10])
+    # a witness that does not satisfy the circuit: the GPU still returns a proof (the prover does not check), the verifier rejects it
+    assert not OG.verify_proof(pk, to_points(zg.create_random_proof(params, MiniCircuit(2, 4, 10, 10), random.Random(7))), [10])
+    params.free()
+
+
 def test_unsatisfied_witness_follows_the_pipeline(ctx):
     """For a witness that does not satisfy the constraints h is not a true quotient; parity then
     depends on following the literal 7-transform pipeline of r1cs_to_qap.rs:144-169."""

@@ -90,6 +90,23 @@ def test_synthetic_mimc_instance(cid):
     assert limbs_to_int(g[:L]) == c.gen[0] * R % c.F.p
 
 
+@pytest.mark.parametrize("cid", [BN254, BLS12_381])
+def test_synthetic_mimc_instance_other_seed_is_satisfied(cid):
+    """every rank of bench.py proves MimcInstance(seed = MIMC_SEED + rank): the matrices must carry the round
+    constants the witness was built with (A z o B z == C z), not the default seed's"""
+    p = FR[cid].p
+    inst = synth.MimcInstance(cid, 32, seed=synth.MIMC_SEED + 3)
+    assert inst.consts != synth.MimcInstance(cid, 32).consts
+
+    def mat_vec(which):
+        rp, cc, _, _ = getattr(inst, which)
+        vals = inst.coeff_ints(which)
+        return [sum(vals[k] * inst.z[cc[k]] for k in range(rp[i], rp[i + 1])) % p for i in range(len(rp) - 1)]
+
+    az, bz, cz = mat_vec("A"), mat_vec("B"), mat_vec("C")
+    assert all(x * y % p == w for x, y, w in zip(az, bz, cz))
+
+
 def test_shard_range_partitions():
     for n in (0, 1, 7, 8, 1 << 24, (1 << 24) + 5):
         for world in (1, 2, 3, 8):
@@ -106,6 +123,7 @@ sys.path.insert(0, %(root)r)
 import numpy as np
 import torch.distributed as dist
 from ckb_zkp_b200 import parallel
+from ckb_zkp_b200.backend import Context
 from oracle.pyref.curves import CURVES
 from oracle.pyref.msm import msm_naive
 from tests import helpers as H
@@ -118,27 +136,40 @@ pts = H.multiples(cid, group, n, start=4)
 pts[5] = None
 sc = [(i * 7919 + 13) ** 5 %% c.r for i in range(n)]
 lo, hi = parallel.shard_range(n, world, rank)
+W = H.points_array(cid, group, [pts[0]])[0].shape[1]
 
-def local_msm(s):          # stands in for ctx.msm on this rank's resident shard
-    P = c.to_affine(msm_naive(c, pts[lo:hi], s))
+def record(P):             # a partial point as a byte record (what zkb_msm_partial hands to a transport)
     xy, inf = H.points_array(cid, group, [P])
-    return xy[0], bool(inf[0])
+    return np.concatenate([xy[0].view(np.uint8), inf.astype(np.uint8)])
 
-def fold(xy, inf):         # stands in for parallel.gpu_fold (EC additions in rank order)
+def partial(scalars=None):  # stands in for ctx.msm_partial on this rank's resident shard
+    return record(c.to_affine(msm_naive(c, pts[lo:hi], sc[lo:hi] if scalars is None else scalars)))
+
+def fold(records):         # stands in for ctx.msm_fold (EC additions in rank order)
     acc = c.identity()
-    for P in H.array_points(cid, group, xy, inf):
+    for rec in records:
+        P = H.array_point(cid, group, np.ascontiguousarray(rec[:8 * W]).view(np.uint64), bool(rec[8 * W]))
         acc = c.add_mixed(acc, P)
-    out, oinf = H.points_array(cid, group, [c.to_affine(acc)])
-    return out[0], bool(oinf[0])
+    return c.to_affine(acc)
 
-got = parallel.msm_sharded(local_msm, fold, sc[lo:hi], world, rank)
-want = c.to_affine(msm_naive(c, pts, sc))
-assert H.array_point(cid, group, got[0], got[1]) == want, (rank, "mismatch")
+got = parallel.msm_sharded_via(partial, fold, parallel.all_gather_bytes, world)
+assert got == c.to_affine(msm_naive(c, pts, sc)), (rank, "mismatch")
 # a rank whose shard sums to the identity must still take part
-zero = parallel.msm_sharded(lambda s: local_msm([0] * (hi - lo)) if rank == 0 else local_msm(s), fold, sc[lo:hi], world, rank)
+zero = parallel.msm_sharded_via(lambda: partial([0] * (hi - lo)) if rank == 0 else partial(), fold,
+                                parallel.all_gather_bytes, world)
 lo1, hi1 = parallel.shard_range(n, world, 1)
-want2 = c.to_affine(msm_naive(c, pts[lo1:hi1], sc[lo1:hi1]))
-assert H.array_point(cid, group, zero[0], zero[1]) == want2
+assert zero == c.to_affine(msm_naive(c, pts[lo1:hi1], sc[lo1:hi1]))
+
+# rendezvous of the library's communicator: rank 0's id reaches every rank unchanged
+class FakeCtx:
+    comm_init_torch = Context.comm_init_torch
+    def comm_unique_id(self):
+        return (np.arange(128, dtype=np.uint8) * 3 + 1).astype(np.uint8)
+    def comm_init(self, n_ranks, rank, unique_id=None):
+        self.got = (n_ranks, rank, None if unique_id is None else np.array(unique_id))
+f = FakeCtx()
+assert f.comm_init_torch() == (world, rank)
+assert f.got[:2] == (world, rank) and np.array_equal(f.got[2], (np.arange(128, dtype=np.uint8) * 3 + 1).astype(np.uint8))
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
