@@ -285,7 +285,7 @@ def sub_msm(args, torch, ctx, world, rank, stream, flush, barrier, tmax, peak):
     for b0 in range(lo - lo % BLK, hi, BLK):
         rng = np.random.default_rng(1000 + b0 // BLK)
         k = synth.random_exponents(rng, BLK)
-        sc = synth.random_exponents(rng, BLK)
+        sc = synth.random_scalars(rng, BLK, CURVE)          # full-width residues mod r
         sl = slice(max(lo, b0) - b0, min(hi, b0 + BLK) - b0)
         k, sc = k[sl], sc[sl]
         xy, inf = ctx.fixed_base_mul(CURVE, 1, gen, k)

@@ -89,6 +89,8 @@ SIGNATURES = {
     "zkb_fr_vec_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_fr_powers": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_spmv": (c_int, [c_void_p, c_int, ctypes.POINTER(Csr), c_void_p, c_size_t, c_void_p]),
+    "zkb_host_keccak_f1600": (None, [c_void_p]),
+    "zkb_host_chacha20_blocks": (None, [c_void_p, c_u64, c_void_p, c_size_t]),
     "zkb_debug_fp_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_debug_pt_op": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t]),
 }

@@ -49,7 +49,7 @@ constexpr int kPairPeriod = 8;
 constexpr uint32_t kPairPeriodUnits = 64;
 __host__ __device__ __forceinline__ uint32_t pair_chunk_units(uint32_t j) {
   // 5, 11, 7, 9, 6, 10, 8, 8 packed in nibbles (lowest nibble = j % 8 == 0)
-  return (0x88A6975Bu >> (4 * (j % kPairPeriod))) & 0xFu;
+  return (0x88A697B5u >> (4 * (j % kPairPeriod))) & 0xFu;
 }
 __host__ __device__ __forceinline__ uint32_t pair_chunk_start_units(uint32_t j) {
   // exclusive prefix sums of the pattern: 0, 5, 16, 23, 32, 38, 48, 56

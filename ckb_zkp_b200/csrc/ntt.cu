@@ -7,11 +7,13 @@ namespace zkb {
 
 // Tile geometry (runtime switches, read once): 2^tile_log elements per shared-memory tile (32 bytes each: 2^10 = 32 KiB,
 // 2^11 = 64 KiB of the 227 KiB an SM offers), later passes read runs of 2^min_run_log contiguous elements.
-// 2^11-element tiles with 64-byte runs turn a 2^21 transform into 11 + 10 stages = TWO passes over HBM instead of three.
+// 2^11-element tiles with 64-byte runs turn a 2^21 transform into 11 + 10 stages = TWO passes over HBM instead of three,
+// but measured slower on B200 (2^21 BLS12-381: 0.550 ms vs 0.519 ms, 2^24: 4.77 vs 4.28 ms, profiles/r2_ntt_geometry.txt):
+// the transform is bound by the multiplier pipe, not by HBM passes, and the larger tile costs occupancy.  Default 2^10 / 2^2.
 struct NttGeom { unsigned tile_log, min_run_log; };
 static NttGeom ntt_geom() {
   static const NttGeom g = []() {
-    NttGeom r{11u, 1u};
+    NttGeom r{10u, 2u};
     if (const char* e = getenv("ZKB_NTT_TILE")) { int v = atoi(e); if (v >= 8 && v <= 12) r.tile_log = (unsigned)v; }
     if (const char* e = getenv("ZKB_NTT_RUN")) { int v = atoi(e); if (v >= 0 && v <= 4) r.min_run_log = (unsigned)v; }
     return r;

@@ -274,8 +274,9 @@ class Index:
             m.to_device(ops.device)
         for star in self.stars.values():
             for key in ("row_evals_on_k", "col_evals_on_k", "val_evals_on_k", "row_evals_on_b", "col_evals_on_b",
-                        "val_evals_on_b", "row_col_evals_on_b"):
-                star[key] = ops.put(star[key])
+                        "val_evals_on_b", "row_col_evals_on_b", "row", "col", "val", "row_col"):
+                if key in star:
+                    star[key] = ops.put(star[key])
         self.resident = True
 
 
@@ -509,3 +510,219 @@ def prover_third_round(st, beta):
     b_poly = trim(o.ifft(o.mul(den[0], o.mul(den[1], den[2])), B))
     h_2 = o.divide_by_vanishing_poly(o.poly_sub(a_poly, o.poly_mul(b_poly, t_poly)), K)[0]
     return [("g_2", g_2, K - 2, None), ("h_2", h_2, None, None)]
+
+
+# ------------------------------------------------------------------------------------------------
+# The crate-level API: universal_setup / index / create_random_proof  (marlin/src/lib.rs:57-181)
+# ------------------------------------------------------------------------------------------------
+from . import fs_rng as _fs          # noqa: E402  (host-side Fiat-Shamir generator and ToBytes layouts)
+from . import kzg10 as _kzg          # noqa: E402
+
+INDEXER_POLYNOMIALS = ["a_row", "a_col", "a_val", "a_row_col", "b_row", "b_col", "b_val", "b_row_col",
+                       "c_row", "c_col", "c_val", "c_row_col"]                      # ahp/mod.rs:34-50
+PROVER_POLYNOMIALS = ["w", "z_a", "z_b", "mask", "t", "g_1", "h_1", "g_2", "h_2"]   # ahp/mod.rs:52-57
+
+
+class IndexTooLarge(Exception):
+    """Error::IndexTooLarge (lib.rs:72-74)"""
+
+
+class UniversalParams:
+    """pc::UniversalParams (pc/data_structures.rs:20-57): powers of beta in G1 (plain and gamma-scaled) and (h, beta h)
+    in G2.  Point arrays in the layout of include/zkb.h."""
+
+    def __init__(self, curve, powers_of_g, powers_of_gamma_g, h, beta_h):
+        self.curve, self.powers_of_g, self.powers_of_gamma_g, self.h, self.beta_h = curve, powers_of_g, powers_of_gamma_g, h, beta_h
+
+    def max_degree(self):
+        return len(self.powers_of_g[1]) - 1
+
+
+def universal_setup(ctx, curve, max_degree, rng):
+    """lib.rs:57-65 -> PC::setup -> KZG10::setup (pc/kzg10.rs:27-72) with the fixed-base multiplications on the GPU
+    (zkb_fixed_base_mul == FixedBaseMSM::multi_scalar_mul + batch_normalization_into_affine).  `rng.randrange` supplies
+    beta and the discrete logs of g, gamma_g, h with respect to the standard generators (the reference draws random group
+    elements through ark's `rand`, a byte stream only a Rust host reproduces; any generators give a valid SRS)."""
+    from . import synth
+    f = Field(curve)
+    p = f.p
+    max_degree = domain_size(max_degree)                       # compute_size_of_domain (lib.rs:61-62)
+    beta = rng.randrange(1, p)
+    kg, kgamma, kh = (rng.randrange(1, p) for _ in range(3))
+    g1, g2 = synth.generator_mont(curve, _lib.G1), synth.generator_mont(curve, _lib.G2)
+
+    def powers(scale):
+        pw = ctx.fr_convert(curve, ctx.fr_powers(curve, f.mont(beta), max_degree + 1, scale_mont=f.mont(scale)), to_mont=False)
+        xs, infs = [], []
+        for i in range(0, len(pw), 1 << 18):
+            xy, inf = ctx.fixed_base_mul(curve, _lib.G1, g1, np.ascontiguousarray(pw[i:i + (1 << 18)]))
+            xs.append(xy)
+            infs.append(inf)
+        return np.concatenate(xs), np.concatenate(infs)
+
+    hs, _ = ctx.fixed_base_mul(curve, _lib.G2, g2, ints_to_limbs([kh, kh * beta % p]))
+    return UniversalParams(curve, powers(kg), powers(kgamma), (hs[0], False), (hs[1], False))
+
+
+class VerifierKey:
+    """pc::VerifierKey (pc/data_structures.rs:102-119)"""
+
+    def __init__(self, curve, g, gamma_g, h, beta_h, supported_degree):
+        self.curve, self.g, self.gamma_g, self.h, self.beta_h, self.supported_degree = curve, g, gamma_g, h, beta_h, supported_degree
+
+    def to_bytes(self):
+        return (b"".join(_fs.affine_to_bytes(self.curve, pt) for pt in (self.g, self.gamma_g, self.h, self.beta_h))
+                + int(self.supported_degree).to_bytes(8, "little"))
+
+
+def pc_trim(ctx, pp, supported_degree):
+    """PC::trim -> KZG10::trim (pc/kzg10.rs:74-98) -> (CommitterKey resident in HBM, VerifierKey)"""
+    if supported_degree > pp.max_degree():
+        raise _kzg.KzgError("TrimmingDegreeTooLarge")
+    n = supported_degree + 1
+    pg = (pp.powers_of_g[0][:n], pp.powers_of_g[1][:n])
+    pgg = (pp.powers_of_gamma_g[0][:n], pp.powers_of_gamma_g[1][:n])
+    ck = _kzg.CommitterKey(ctx, pp.curve, pg, pgg, supported_degree)
+    vk = VerifierKey(pp.curve, (pg[0][0], bool(pg[1][0])), (pgg[0][0], bool(pgg[1][0])), pp.h, pp.beta_h, supported_degree)
+    return ck, vk
+
+
+class IndexVerifierKey:
+    """data_structures.rs:10-33"""
+
+    def __init__(self, curve, index_info, index_comms, verifier_key):
+        self.curve, self.index_info, self.index_comms, self.verifier_key = curve, index_info, index_comms, verifier_key
+
+    def to_bytes(self):
+        """ToBytes (data_structures.rs:22-33): index_info, u32 count, the commitments, the verifier key"""
+        return (_fs.index_info_to_bytes(*self.index_info) + len(self.index_comms).to_bytes(4, "little")
+                + _fs.commitments_to_bytes(self.curve, self.index_comms) + self.verifier_key.to_bytes())
+
+
+class IndexProverKey:
+    """data_structures.rs:35-41"""
+
+    def __init__(self, index, index_rands, index_verifier_key, committer_key, extra_vars=0):
+        self.index, self.index_rands, self.index_verifier_key, self.committer_key = index, index_rands, index_verifier_key, committer_key
+        self.extra_vars = extra_vars           # padding witness variables make_matrices_square appends (constraint_systems.rs:9-31)
+        self.refresh_polys()
+
+    def refresh_polys(self):
+        """Index::iter (indexer.rs:51-67): the twelve labeled index polynomials, on whichever side the index lives"""
+        self.index_polys = [_kzg.LabeledPolynomial(label, self.index.stars[label[0]][label[2:]], None, None)
+                            for label in INDEXER_POLYNOMIALS]
+
+
+class Proof:
+    """data_structures.rs:43-48: commitments per round, the evaluations in query-set order, the opening proofs"""
+
+    def __init__(self, commitments, evaluations, opening_proofs):
+        self.commitments, self.evaluations, self.opening_proofs = commitments, evaluations, opening_proofs
+
+
+def ahp_max_degree(num_constraints, num_variables, num_non_zeros):
+    """AHP::max_degree (ahp/mod.rs:66-84)"""
+    h, k = domain_size(max(num_constraints, num_variables)), domain_size(num_non_zeros)
+    return max(3 * h + 2 * 1 - 1, 3 * k - 3)
+
+
+def _synthesize(curve, circuit):
+    """ConstraintSynthesizer -> (A, B, C CsrMatrix, formatted input ints or Montgomery array, witness, n_inputs).
+    `circuit` either implements generate_constraints(cs) against the zkp_r1cs interface (r1cs.py), or -- for large
+    synthetic instances built as arrays -- exposes marlin_arrays(ctx) -> (A, B, C, x_mont, w_mont)."""
+    from .r1cs import ProvingAssignment
+    pa = ProvingAssignment(FR_MODULUS[curve])
+    pa.alloc_input(1)
+    circuit.generate_constraints(pa)
+    return pa
+
+
+def _matrices_and_assignment(ctx, curve, circuit):
+    if hasattr(circuit, "marlin_arrays"):
+        return circuit.marlin_arrays(ctx)
+    pa = _synthesize(curve, circuit)
+    mats = []
+    for which in "abc":
+        ptr, cols, coeffs = pa.csr(which)
+        mats.append(CsrMatrix(ptr, cols, ctx.fr_convert(curve, ints_to_limbs(coeffs), to_mont=True)))
+    x = ctx.fr_convert(curve, ints_to_limbs(pa.input_assignment), to_mont=True)
+    w = ctx.fr_convert(curve, ints_to_limbs(pa.aux_assignment), to_mont=True)
+    return mats[0], mats[1], mats[2], x, w
+
+
+def index_keys(ctx, srs, circuit):
+    """zkp_marlin::index (lib.rs:67-95): AHP::index, PC::trim, PC::commit of the twelve index polynomials (not hiding)
+    -> (IndexProverKey, IndexVerifierKey)"""
+    curve = srs.curve
+    a, b, c, x, w = _matrices_and_assignment(ctx, curve, circuit)
+    idx, extra = index(ctx, curve, a, b, c, len(x), len(x) + len(w))
+    max_degree = ahp_max_degree(idx.num_constraints, idx.num_variables, idx.num_non_zeros)
+    if srs.max_degree() < max_degree:
+        raise IndexTooLarge()
+    ck, vk = pc_trim(ctx, srs, max_degree)
+    ipk = IndexProverKey(idx, None, None, ck, extra)
+    comms, rands = _kzg.pc_commit(ck, ipk.index_polys, None)
+    ivk = IndexVerifierKey(curve, (idx.num_variables, idx.num_constraints, idx.num_non_zeros), comms, vk)
+    ipk.index_rands, ipk.index_verifier_key = rands, ivk
+    return ipk, ivk
+
+
+def sample_element_outside_domain(f, size, rng):
+    """ahp/verifier.rs:117-126"""
+    t = rng.rand_fr()
+    while f.vanishing_at(size, t) == 0:
+        t = rng.rand_fr()
+    return t
+
+
+def verifier_query_set(beta, gamma):
+    """ahp/verifier.rs:90-115 in BTreeSet order: sorted by label (every label occurs once)"""
+    at_beta = ["w", "z_a", "z_b", "mask", "t", "g_1", "h_1"]
+    return sorted([(l, beta) for l in at_beta] + [(l, gamma) for l in ["g_2", "h_2"] + INDEXER_POLYNOMIALS])
+
+
+def create_random_proof(ctx, ipk, circuit, zk_rng, fs_rng=None, resident=True):
+    """zkp_marlin::create_random_proof (lib.rs:97-181).  zk_rng: the prover's randomness (randrange(p); optional
+    field_array(n) for bulk draws); fs_rng: the Fiat-Shamir generator -- fs_rng.FiatShamirRng (marlin/src/fs_rng.rs
+    restated) seeded as lib.rs:105-106 when None, or any object with absorb(bytes) / rand_fr() / rand_u128()."""
+    idx, ck, ivk = ipk.index, ipk.committer_key, ipk.index_verifier_key
+    curve = idx.curve
+    f = Field(curve)
+    a, b, c, x, w = _matrices_and_assignment(ctx, curve, circuit)
+    if ipk.extra_vars:                  # make_matrices_square's padding variables carry F::one() (constraint_systems.rs:15-19)
+        w = np.concatenate([np.ascontiguousarray(w), np.tile(f.mont(1), (ipk.extra_vars, 1))])
+    st = prover_init(ctx, idx, x, w, resident=resident)
+    if resident:                        # the index polynomials moved into HBM with the rest of the index
+        ipk.refresh_polys()
+    public_input = np.ascontiguousarray(x)[1:]
+    if fs_rng is None:
+        fs_rng = _fs.FiatShamirRng(ivk.to_bytes() + _fs.fr_mont_array_to_bytes(ctx, curve, public_input), curve)
+    labeled, comms_by_round, rands = list(ipk.index_polys), [], list(ipk.index_rands)
+
+    def commit(round_polys):
+        polys = [_kzg.LabeledPolynomial(label, poly, db, hb) for label, poly, db, hb in round_polys]
+        cs, rs = _kzg.pc_commit(ck, polys, zk_rng)                      # lib.rs:109-110,117-118,124-125
+        labeled.extend(polys)
+        rands.extend(rs)
+        comms_by_round.append(cs)
+        fs_rng.absorb(_fs.commitments_to_bytes(curve, cs))             # lib.rs:112,120,127
+
+    commit(prover_first_round(st, zk_rng))
+    alpha = sample_element_outside_domain(f, idx.h_size, fs_rng)       # verifier_first_round (ahp/verifier.rs:40-70)
+    eta_a, eta_b, eta_c = fs_rng.rand_fr(), fs_rng.rand_fr(), fs_rng.rand_fr()
+    commit(prover_second_round(st, alpha, eta_a, eta_b, eta_c))
+    beta = sample_element_outside_domain(f, idx.h_size, fs_rng)        # verifier_second_round (:72-80)
+    commit(prover_third_round(st, beta))
+    gamma = fs_rng.rand_fr()                                           # verifier_third_round (:82-88)
+
+    query_set = verifier_query_set(beta, gamma)
+    by_label = {P.label: P for P in labeled}
+    points = {beta: f.mont(beta), gamma: f.mont(gamma)}
+    evaluations = [ctx.poly_eval(curve, by_label[label].coeffs, points[pt]) for label, pt in query_set]   # lib.rs:147-156
+    fs_rng.absorb(_fs.fr_mont_array_to_bytes(ctx, curve, np.stack(evaluations)))                          # lib.rs:157
+    opening_challenge = fs_rng.rand_u128()                             # u128::rand(&mut fs_rng).into() (lib.rs:158)
+    opening_proofs = _kzg.pc_batch_open(ck, labeled, query_set, opening_challenge, rands)                 # lib.rs:160-166
+    proof = Proof(comms_by_round, evaluations, opening_proofs)
+    proof.challenges = {"alpha": alpha, "eta_a": eta_a, "eta_b": eta_b, "eta_c": eta_c, "beta": beta, "gamma": gamma,
+                        "opening_challenge": opening_challenge}       # not part of the reference's Proof: kept for the tests
+    return proof

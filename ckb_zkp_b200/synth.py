@@ -159,6 +159,14 @@ def random_exponents(rng, n):
     return k
 
 
+def random_scalars(rng, n, curve):
+    """n pseudo-random FULL-WIDTH scalars below the curve's Fr modulus as uint64[n, 4] (top limb drawn below the
+    modulus' top limb: every window of the Pippenger decomposition is populated, including the last one)"""
+    k = rng.integers(0, np.iinfo(np.uint64).max, size=(n, 4), dtype=np.uint64, endpoint=True)
+    k[:, 3] = rng.integers(0, FR_MODULUS[curve] >> 192, size=n, dtype=np.uint64)
+    return k
+
+
 def limbs_to_ints(arr):
     raw = np.ascontiguousarray(arr, dtype=np.uint64).tobytes()
     w = arr.shape[1] * 8

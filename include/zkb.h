@@ -257,6 +257,12 @@ int zkb_fr_powers(zkb_ctx* ctx, int curve, const uint64_t base_mont[4], const ui
  * marlin/src/ahp/prover.rs:110-123 (z_A, z_B) and :259-269 (t, with the transposed matrices) */
 int zkb_spmv(zkb_ctx* ctx, int curve, const zkb_csr* m, const uint64_t* x_mont, size_t n_cols, uint64_t* y_mont);
 
+/* ---- host-side helpers of the Python host layer (no device work, usable without a GPU) ----------------------
+ * marlin/src/fs_rng.rs builds its Fiat-Shamir generator from merlin (STROBE-128 over Keccak-f[1600]) and rand_chacha
+ * (ChaCha20); a Rust host links those crates, the Python host layer (ckb_zkp_b200/fs_rng.py) uses these two. */
+void zkb_host_keccak_f1600(uint64_t state[25]);
+void zkb_host_chacha20_blocks(const uint8_t key[32], uint64_t counter, uint32_t* out_words, size_t n_blocks);
+
 /* ---- diagnostics: single field / group operations of the device arithmetic on n operands, used by
  * the parity tests to check the GPU arithmetic against the CPU oracle in isolation.
  * field: 0 BN254 Fr, 1 BLS12-381 Fr, 2 BN254 Fq, 3 BLS12-381 Fq.

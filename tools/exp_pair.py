@@ -34,7 +34,7 @@ for group in a.groups:
         xy, inf = ctx.fixed_base_mul(1, group, gen, synth.random_exponents(rng, min(1 << 18, n - i)))
         xs.append(xy); infs.append(inf)
     srs = ctx.srs_upload(1, group, np.concatenate(xs), np.concatenate(infs))
-    d = torch.from_numpy(synth.random_exponents(rng, n).view(np.int64)).cuda()
+    d = torch.from_numpy(synth.random_scalars(rng, n, 1).view(np.int64)).cuda()
     base = None
     for lv in a.levels:
         for sc in (a.scales if lv else [0]):

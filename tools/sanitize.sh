@@ -14,7 +14,7 @@ for tool in $TOOLS; do
   [ "$tool" = initcheck ] && extra="--track-unused-memory no"
   args=""
   # racecheck serialises shared-memory accesses: keep its workload to the small shapes
-  [ "$tool" = racecheck ] && args="--small"
+  [ "$tool" = racecheck ] && [ -n "${SMALL:-}" ] && args="--small"
   start=$(date +%s)
   timeout "$TMO" "$CS" --tool "$tool" $extra --print-limit 40 --error-exitcode 7 python tools/sanitize_target.py $args \
       > "$OUT/$tool.log" 2>&1
