@@ -15,6 +15,7 @@ G1, G2 = 1, 2
 NTT_INVERSE, NTT_COSET = 1, 2
 SRS_PRECOMPUTE = 1
 COMM_ID_BYTES = 128
+DECOMPRESS_CHECK_SUBGROUP = 1
 
 OK, E_INVALID, E_CUDA, E_TOO_LARGE, E_NO_DEVICE = 0, -1, -2, -3, -4
 
@@ -82,6 +83,7 @@ SIGNATURES = {
                                           c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zkb_groth16_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zkb_fixed_base_mul": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "zkb_points_decompress": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_uint, c_void_p, c_void_p, c_void_p]),
     "zkb_fr_convert": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "zkb_poly_div_linear": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zkb_poly_lincomb": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),

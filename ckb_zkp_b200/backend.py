@@ -78,6 +78,7 @@ class CsrMatrix:
             raise ValueError("row_ptr needs n_rows + 1 entries")
         if len(self.col_idx) != len(self.coeff) or int(self.row_ptr[-1]) != len(self.col_idx):
             raise ValueError("inconsistent CSR arrays")
+        self.max_col = int(self.col_idx.max()) if len(self.col_idx) else -1     # checked against the vector length by spmv
         self.c = Csr(len(self.row_ptr) - 1, len(self.col_idx), self.row_ptr.ctypes.data, self.col_idx.ctypes.data,
                      self.coeff.ctypes.data)
 
@@ -304,6 +305,19 @@ class Context:
         self._check(self.lib.zkb_msm_fold(self.handle, curve, group, _ptr(partials), partials.shape[0], _ptr(out), _ptr(oinf)))
         return out, bool(oinf[0])
 
+    def points_decompress(self, curve, group, compressed, check_subgroup=False):
+        """ark-serialize compressed points (uint8[n, bytes]) -> (xy uint64[n, words], inf uint8[n], status uint8[n])"""
+        w = point_words(curve, group)
+        data = np.ascontiguousarray(compressed, dtype=np.uint8).reshape(-1, w * 4)
+        n = data.shape[0]
+        xy = np.zeros((n, w), dtype=np.uint64)
+        inf = np.zeros(n, dtype=np.uint8)
+        status = np.zeros(n, dtype=np.uint8)
+        self._check(self.lib.zkb_points_decompress(self.handle, curve, group, _ptr(data), n,
+                                                   _lib.DECOMPRESS_CHECK_SUBGROUP if check_subgroup else 0, _ptr(xy), _ptr(inf),
+                                                   _ptr(status)))
+        return xy, inf, status
+
     # -- NTT ----------------------------------------------------------------------------------
     def ntt(self, curve, data, log_n, inverse=False, coset=False):
         """In-place transform of uint64[2^log_n, 4] (Montgomery), natural order in and out."""
@@ -390,6 +404,8 @@ class Context:
 
     def spmv(self, curve, m, x_mont):
         x = _fr(x_mont, "x")
+        if m.max_col >= x.shape[0]:          # the kernel reads x[col] unchecked: a malformed matrix must not reach the device
+            raise ValueError("CSR column index %d out of range for a vector of %d elements" % (m.max_col, x.shape[0]))
         y = _out_like(x, m.n_rows)
         self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), _addr(x), x.shape[0], _addr(y)))
         return y

@@ -417,6 +417,33 @@ int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_
   return ZKB_OK;
 }
 
+// ---- key-file ingestion ------------------------------------------------------------------------
+int zkb_points_decompress(zkb_ctx* ctx, int curve, int group, const uint8_t* compressed, size_t n, unsigned flags,
+                          uint64_t* out_xy_mont, uint8_t* out_inf, uint8_t* out_status) {
+  if (!ctx || (n && (!compressed || !out_xy_mont || !out_inf || !out_status))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  const GroupOps* ops = group_ops(curve, group);
+  if (!ops) return set_err(ctx, ZKB_E_INVALID, "points_decompress: unknown curve %d / group %d", curve, group);
+  if (n >= (size_t(1) << 31)) return set_err(ctx, ZKB_E_INVALID, "points_decompress: too many points");
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  const size_t in_bytes = ops->affine_bytes / 2;          // x only
+  Scratch ws(ctx, st);
+  uint8_t *d_in, *d_xy, *d_inf, *d_status;
+  ZKB_TRY(ws.alloc(&d_in, n * in_bytes));
+  ZKB_TRY(ws.alloc(&d_xy, n * ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_inf, n));
+  ZKB_TRY(ws.alloc(&d_status, n));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, compressed, n * in_bytes, cudaMemcpyDefault, st));
+  ZKB_TRY(ops->decompress(ctx, st, d_in, n, (flags & ZKB_DECOMPRESS_CHECK_SUBGROUP) ? 1 : 0, d_xy, d_inf, d_status));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy_mont, d_xy, n * ops->affine_bytes, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, n, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_status, d_status, n, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 // ---- Fr helpers ------------------------------------------------------------------------------
 int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode) {
   if (!ctx || (n && (!in || !out)) || (mode != 0 && mode != 1)) return ZKB_E_INVALID;

@@ -3,6 +3,7 @@
 // four heavy instantiations compile in parallel.
 #pragma once
 #include "msm.cuh"
+#include "serialize.cuh"
 
 namespace zkb {
 
@@ -24,6 +25,37 @@ k_fixed_base_mul(const Affine<F>* __restrict__ base, const uint32_t* __restrict_
   out_inf[i] = r.is_inf() ? 1 : 0;
 }
 
+// ark-serialize compressed points -> affine Montgomery (serialize.cuh); one thread per point, the curve coefficient
+// is derived once per block.  check_subgroup: r * P == 0 (255 doublings per point: only when the caller asks).
+template <class F, class FrP>
+__global__ void __launch_bounds__(128)
+k_decompress(const uint8_t* __restrict__ in, uint32_t n, int check_subgroup, Affine<F>* __restrict__ out_xy,
+             uint8_t* __restrict__ out_inf, uint8_t* __restrict__ out_status) {
+  __shared__ F b_sh;
+  if (threadIdx.x == 0) b_sh = curve_b((const F*)nullptr);
+  __syncthreads();
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint8_t bytes[sizeof(F)];
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)i * sizeof(F));      // sizeof(F) is a multiple of 16
+#pragma unroll
+  for (int k = 0; k < (int)(sizeof(F) / 16); k++) reinterpret_cast<uint4*>(bytes)[k] = __ldg(src + k);
+  Affine<F> p;
+  bool is_inf = false;
+  uint8_t st = decompress_point(bytes, b_sh, p, is_inf);
+  if (st == kDecompOk && !is_inf && check_subgroup) {
+    uint32_t r[kScalarLimbs];
+#pragma unroll
+    for (int k = 0; k < kScalarLimbs; k++) r[k] = FrP::mod(k);
+    XYZZ<F> q = XYZZ<F>::mul_limbs(XYZZ<F>::from_affine(p), r, kScalarLimbs);
+    if (!q.is_inf()) st = kDecompNotInSubgroup;
+  }
+  if (st != kDecompOk) { p = Affine<F>::inf(); is_inf = true; }
+  st_vec(&out_xy[i], p);
+  out_inf[i] = is_inf ? 1 : 0;
+  out_status[i] = st;
+}
+
 template <class F, class FrP>
 struct GroupImpl {
   using E = MsmEngine<F, FrP>;
@@ -41,9 +73,16 @@ struct GroupImpl {
                (Affine<F>*)d_out_affine, d_out_inf);
     return ZKB_OK;
   }
+  static int decompress(zkb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, size_t n, int check_subgroup, void* d_xy,
+                        uint8_t* d_inf, uint8_t* d_status) {
+    if (n == 0) return ZKB_OK;
+    ZKB_LAUNCH(ctx, (k_decompress<F, FrP>), ceil_div(n, 128), 128, 0, st, d_in, (uint32_t)n, check_subgroup, (Affine<F>*)d_xy,
+               d_inf, d_status);
+    return ZKB_OK;
+  }
   static const GroupOps* ops() {
     static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host,
-                               &fixed_base_mul, &fold};
+                               &fixed_base_mul, &fold, &decompress};
     return &o;
   }
 };

@@ -888,6 +888,9 @@ struct GroupOps {
   // canonical affine d_out_affine + d_out_inf (may be null)
   int (*fold)(zkb_ctx*, cudaStream_t, const void* d_points, uint32_t count, uint32_t stride_bytes, void* d_out_pt,
               void* d_out_affine, uint8_t* d_out_inf);
+  // ark-serialize compressed points (affine_bytes / 2 bytes each) -> affine Montgomery + identity flags + per-point status
+  int (*decompress)(zkb_ctx*, cudaStream_t, const uint8_t* d_in, size_t n, int check_subgroup, void* d_out_affine,
+                    uint8_t* d_out_inf, uint8_t* d_out_status);
 };
 const GroupOps* group_ops(int curve, int group);
 

@@ -68,16 +68,32 @@ def _leading_zeros(p):
 
 
 class CommitterKey:
-    """data_structures.rs:59-100 resident on one GPU."""
+    """data_structures.rs:59-100 resident on one GPU -- or, with shard = (n_ranks, rank), one contiguous slice of
+    powers_of_g per GPU: every rank then runs the same prover (same polynomials, same randomness) and each commitment /
+    opening MSM is computed from the ranks' partial sums with one ncclAllGather inside the library (zkb_msm_sharded);
+    all ranks obtain the identical commitment, so the Fiat-Shamir transcripts stay in step without further exchange.
+    The hiding key powers_of_gamma_g is only ever used for hiding_bound + 1 <= 2 terms and stays whole on every rank."""
 
-    def __init__(self, ctx, curve, powers_of_g, powers_of_gamma_g, supported_degree=None):
-        """powers_*: (xy uint64[n, words], inf uint8[n]) in the layout of include/zkb.h"""
-        self.ctx, self.curve = ctx, curve
+    def __init__(self, ctx, curve, powers_of_g, powers_of_gamma_g, supported_degree=None, shard=None):
+        """powers_*: (xy uint64[n, words], inf uint8[n]) in the layout of include/zkb.h (the WHOLE key on every rank)"""
+        self.ctx, self.curve, self.shard = ctx, curve, shard
         self.n = len(powers_of_g[1])
         self.supported_degree = self.n - 1 if supported_degree is None else supported_degree
-        self.g = ctx.srs_upload(curve, _lib.G1, powers_of_g[0], powers_of_g[1])
-        self.gamma_g = ctx.srs_upload(curve, _lib.G1, powers_of_gamma_g[0], powers_of_gamma_g[1])
+        if shard is None:
+            self.g = ctx.srs_upload(curve, _lib.G1, powers_of_g[0], powers_of_g[1])
+        else:
+            from .parallel import shard_range
+            lo, hi = shard_range(self.n, shard[0], shard[1])
+            self.g = ctx.srs_upload_shard(curve, _lib.G1, powers_of_g[0][lo:hi], powers_of_g[1][lo:hi], lo, self.n)
+        n_hiding = self.n_hiding = min(self.n, 1024)
+        self.gamma_g = ctx.srs_upload(curve, _lib.G1, powers_of_gamma_g[0][:n_hiding], powers_of_gamma_g[1][:n_hiding])
         self.to_mont = lambda ints: ctx.fr_convert(curve, ints_to_limbs(ints), to_mont=True)
+
+    def msm_g(self, scalars_mont, base_offset=0):
+        """multi_scalar_mul(&powers_of_g[base_offset..], scalars) with Montgomery scalars (into_repr fused)"""
+        if self.shard is None:
+            return self.ctx.msm(self.g, scalars_mont, base_offset=base_offset, mont=True)
+        return self.ctx.msm_sharded(self.g, scalars_mont, base_offset=base_offset, mont=True)
 
     def free(self):
         self.g.free()
@@ -133,14 +149,14 @@ def kzg_commit(ck, p, hiding_bound=None, rng=None, base_offset=0, supported_degr
     if deg > sup:
         raise DegreeOutOfBound()
     nz = _leading_zeros(p)                                       # skip_leading_zeros_and_convert_to_bigints
-    comm = ctx.msm(ck.g, p[nz:], base_offset=base_offset + nz, mont=True)
+    comm = ck.msm_g(p[nz:], base_offset + nz)
     rand = Randomness()
     if hiding_bound is not None:
         if rng is None:
             raise MissingRng()
         if hiding_bound == 0:
             raise HidingBoundIsZero()
-        if hiding_bound > ck.n - base_offset:
+        if hiding_bound > ck.n - base_offset or hiding_bound + 1 > ck.n_hiding:
             raise HidingBoundTooLarge()
         rand = Randomness.rand(ck, hiding_bound, rng)
         rc = ctx.msm(ck.gamma_g, rand.blinding, mont=True)
@@ -158,7 +174,7 @@ def kzg_open(ck, p, point_mont, rand):
         raise DegreeOutOfBound()
     witness, _ = ctx.poly_div_linear(ck.curve, p, point_mont)    # compute_witness_polynomial :211-226
     nz = _leading_zeros(witness)
-    w = ctx.msm(ck.g, witness[nz:], base_offset=nz, mont=True)
+    w = ck.msm_g(witness[nz:], nz)
     rand_v = None
     if rand.is_hiding():
         rq, rand_v = ctx.poly_div_linear(ck.curve, rand.blinding, point_mont)

@@ -124,10 +124,19 @@ class Ops:
         pointers and only the few scalars that feed the transcript travel to the host.  torch's current stream is
         pointed at the library's stream so tensor glue (slicing, concatenation, zero fill) and kernels stay ordered."""
         self.ctx, self.curve, self.f = ctx, curve, Field(curve)
-        self.device = None
+        self.device, self._prev_stream = None, None
         if resident:
             self.device = torch.device("cuda", torch.cuda.current_device())
+            self._prev_stream = torch.cuda.current_stream(self.device)
             torch.cuda.set_stream(torch.cuda.ExternalStream(ctx.stream, device=self.device))
+
+    def release(self):
+        """give torch's current stream back to the caller (create_random_proof does this when the proof is done; callers of
+        the round-level API with resident=True call it themselves once they are finished with the round state)"""
+        if self._prev_stream is not None:
+            self.ctx.sync()
+            torch.cuda.set_stream(self._prev_stream)
+            self._prev_stream = None
 
     # array plumbing on whichever side the vectors live
     def zeros(self, n):
@@ -575,14 +584,15 @@ class VerifierKey:
                 + int(self.supported_degree).to_bytes(8, "little"))
 
 
-def pc_trim(ctx, pp, supported_degree):
-    """PC::trim -> KZG10::trim (pc/kzg10.rs:74-98) -> (CommitterKey resident in HBM, VerifierKey)"""
+def pc_trim(ctx, pp, supported_degree, shard=None):
+    """PC::trim -> KZG10::trim (pc/kzg10.rs:74-98) -> (CommitterKey resident in HBM, VerifierKey).
+    shard = (n_ranks, rank): powers_of_g sliced over the ranks (kzg10.CommitterKey)"""
     if supported_degree > pp.max_degree():
         raise _kzg.KzgError("TrimmingDegreeTooLarge")
     n = supported_degree + 1
     pg = (pp.powers_of_g[0][:n], pp.powers_of_g[1][:n])
     pgg = (pp.powers_of_gamma_g[0][:n], pp.powers_of_gamma_g[1][:n])
-    ck = _kzg.CommitterKey(ctx, pp.curve, pg, pgg, supported_degree)
+    ck = _kzg.CommitterKey(ctx, pp.curve, pg, pgg, supported_degree, shard=shard)
     vk = VerifierKey(pp.curve, (pg[0][0], bool(pg[1][0])), (pgg[0][0], bool(pgg[1][0])), pp.h, pp.beta_h, supported_degree)
     return ck, vk
 
@@ -650,16 +660,17 @@ def _matrices_and_assignment(ctx, curve, circuit):
     return mats[0], mats[1], mats[2], x, w
 
 
-def index_keys(ctx, srs, circuit):
+def index_keys(ctx, srs, circuit, shard=None):
     """zkp_marlin::index (lib.rs:67-95): AHP::index, PC::trim, PC::commit of the twelve index polynomials (not hiding)
-    -> (IndexProverKey, IndexVerifierKey)"""
+    -> (IndexProverKey, IndexVerifierKey).  shard = (n_ranks, rank): one process per GPU, the committer key sliced over
+    the ranks; index_keys and create_random_proof are then collective calls with identical arguments on every rank."""
     curve = srs.curve
     a, b, c, x, w = _matrices_and_assignment(ctx, curve, circuit)
     idx, extra = index(ctx, curve, a, b, c, len(x), len(x) + len(w))
     max_degree = ahp_max_degree(idx.num_constraints, idx.num_variables, idx.num_non_zeros)
     if srs.max_degree() < max_degree:
         raise IndexTooLarge()
-    ck, vk = pc_trim(ctx, srs, max_degree)
+    ck, vk = pc_trim(ctx, srs, max_degree, shard=shard)
     ipk = IndexProverKey(idx, None, None, ck, extra)
     comms, rands = _kzg.pc_commit(ck, ipk.index_polys, None)
     ivk = IndexVerifierKey(curve, (idx.num_variables, idx.num_constraints, idx.num_non_zeros), comms, vk)
@@ -692,6 +703,16 @@ def create_random_proof(ctx, ipk, circuit, zk_rng, fs_rng=None, resident=True):
     if ipk.extra_vars:                  # make_matrices_square's padding variables carry F::one() (constraint_systems.rs:15-19)
         w = np.concatenate([np.ascontiguousarray(w), np.tile(f.mont(1), (ipk.extra_vars, 1))])
     st = prover_init(ctx, idx, x, w, resident=resident)
+    try:
+        return _create_random_proof(ctx, ipk, st, x, zk_rng, fs_rng, resident)
+    finally:
+        st.ops.release()                # torch's current stream goes back to the caller
+
+
+def _create_random_proof(ctx, ipk, st, x, zk_rng, fs_rng, resident):
+    idx, ck, ivk = ipk.index, ipk.committer_key, ipk.index_verifier_key
+    curve = idx.curve
+    f = Field(curve)
     if resident:                        # the index polynomials moved into HBM with the rest of the index
         ipk.refresh_polys()
     public_input = np.ascontiguousarray(x)[1:]

@@ -224,6 +224,17 @@ int zkb_groth16_fold(zkb_ctx* ctx, const zkb_pk* pk, const void* partials, size_
 int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_xy_mont,
                        const uint64_t* scalars_canonical, size_t n, uint64_t* out_xy, uint8_t* out_inf);
 
+/* ---- key-file ingestion: ark-serialize 0.2 compressed points -> the ABI's point layout --------------------------
+ * What `Parameters::<E>::deserialize` (groth16/src/lib.rs:81; cli/src/zkp_prove.rs:117-124) and the Marlin key types do
+ * per point in ark-ec's `GroupAffine::deserialize`: x as canonical little-endian bytes (Fq2: c0 then c1; 32 / 48 bytes
+ * per Fq), flags in the two top bits of the last byte (bit 7: y is the larger root, bit 6: infinity); y is recovered
+ * with the Fq / Fq2 square root on the device.  out_status[i]: 0 ok, 1 coordinate not canonical (>= p), 2 x not on the
+ * curve, 3 not in the prime-order subgroup (only with ZKB_DECOMPRESS_CHECK_SUBGROUP); a rejected point is returned as
+ * the identity.  Buffers may be host or device memory.  The result feeds zkb_srs_upload / zkb_groth16_pk_create. */
+#define ZKB_DECOMPRESS_CHECK_SUBGROUP 1u
+int zkb_points_decompress(zkb_ctx* ctx, int curve, int group, const uint8_t* compressed, size_t n, unsigned flags,
+                          uint64_t* out_xy_mont, uint8_t* out_inf, uint8_t* out_status);
+
 /* ---- Fr helpers (device-side batch ops on host arrays; used by the host layers) ------------ */
 /* out[i] = into_repr(in[i]) (mode 0) or from_repr(in[i]) (mode 1) */
 int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode);

@@ -4,6 +4,7 @@
 // a GPU.  Test infrastructure only; not linked into the product library.
 #include <cstring>
 #include "../../ckb_zkp_b200/csrc/curve.cuh"
+#include "../../ckb_zkp_b200/csrc/serialize.cuh"
 
 using namespace zkb;
 
@@ -53,6 +54,24 @@ template <class F> static void pt_op(int op, const uint32_t* acc, const uint32_t
   }
 }
 
+// point decompression (serialize.cuh): bytes -> affine Montgomery limbs; returns the kDecomp* status, *inf = identity flag.
+// check_subgroup: r * P == 0 with the scalar-field modulus limbs, like the device kernel.
+template <class F, class FrP> static int decompress_one(const uint8_t* bytes, int check_subgroup, uint32_t* out, uint8_t* inf) {
+  Affine<F> p;
+  bool is_inf = false;
+  F b = curve_b((const F*)nullptr);
+  uint8_t st = decompress_point(bytes, b, p, is_inf);
+  if (st == kDecompOk && !is_inf && check_subgroup) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; i++) r[i] = FrP::mod(i);
+    XYZZ<F> q = XYZZ<F>::mul_limbs(XYZZ<F>::from_affine(p), r, 8);
+    if (!q.is_inf()) st = kDecompNotInSubgroup;
+  }
+  memcpy(out, &p, sizeof(p));
+  *inf = is_inf ? 1 : 0;
+  return st;
+}
+
 extern "C" {
 // field: 0 BnFr, 1 BlsFr, 2 BnFq, 3 BlsFq, 4 BnFq2, 5 BlsFq2
 void emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -80,5 +99,13 @@ void emu_pt_op(int curve, int group, int op, const uint32_t* acc, const uint32_t
   if (curve == 0 && group == 2) pt_op<Fp2<BnFq>>(op, acc, q, neg, out);
   if (curve == 1 && group == 1) pt_op<Fp<BlsFq>>(op, acc, q, neg, out);
   if (curve == 1 && group == 2) pt_op<Fp2<BlsFq>>(op, acc, q, neg, out);
+}
+
+int emu_decompress(int curve, int group, const uint8_t* bytes, int check_subgroup, uint32_t* out, uint8_t* inf) {
+  if (curve == 0 && group == 1) return decompress_one<Fp<BnFq>, BnFr>(bytes, check_subgroup, out, inf);
+  if (curve == 0 && group == 2) return decompress_one<Fp2<BnFq>, BnFr>(bytes, check_subgroup, out, inf);
+  if (curve == 1 && group == 1) return decompress_one<Fp<BlsFq>, BlsFr>(bytes, check_subgroup, out, inf);
+  if (curve == 1 && group == 2) return decompress_one<Fp2<BlsFq>, BlsFr>(bytes, check_subgroup, out, inf);
+  return -1;
 }
 }

@@ -11,7 +11,7 @@ TMO=${TMO:-1500}
 for tool in $TOOLS; do
   extra=""
   [ "$tool" = racecheck ] && extra="--racecheck-report all"
-  [ "$tool" = initcheck ] && extra="--track-unused-memory no"
+  :
   args=""
   # racecheck serialises shared-memory accesses: keep its workload to the small shapes
   [ "$tool" = racecheck ] && [ -n "${SMALL:-}" ] && args="--small"
