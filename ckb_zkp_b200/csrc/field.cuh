@@ -378,6 +378,131 @@ struct alignas(16) Fp {
     for (int i = 0; i < N; i++) r.v[i] = x2[i];
     return mul(mul(r, r2()), r2());
   }
+  // ---- a^-1 by Bernstein-Yang division steps in batches of 30 ("safegcd", the half-delta variant) --------------
+  // Same contract as inv() (Montgomery in, Montgomery out, 0 -> 0), ~5x fewer instructions: the 30 division steps of a
+  // batch look only at the low 30 bits of (f, g) and produce a 2x2 transition matrix t with |entries| <= 2^30, which is
+  // then applied to the full-width (f, g) and, modulo p, to (d, e) -- 10 signed 32x32->64 multiply-adds per 30-bit limb
+  // and batch instead of ~190 add/logic instructions per bit.  Values are signed, L = ceil((BITS + 2) / 30) limbs of
+  // 30 bits (top limb carries the sign); invariants d * x == f, e * x == g (mod p) up to the common power of two that
+  // the modular update divides out.  Terminates when g == 0 (f = +-1); the step bound of the half-delta rule for a
+  // BITS-bit modulus is below 49 * BITS / 17 + 4 steps, kMaxBatches covers it.  The batched-affine bucket accumulation
+  // (msm_batch.cuh) runs one of these per thread and round, so its length decides how many buckets a thread must own.
+  static constexpr int L30 = (P::BITS + 2 + 29) / 30;
+  static constexpr int kMaxBatches = (49 * P::BITS / 17 + 4 + 29) / 30;
+  ZKB_HD static constexpr int32_t mod30(int i) {            // limb i of p in base 2^30
+    const int bit = 30 * i, w = bit >> 5, s = bit & 31;
+    uint64_t x = w < N ? (uint64_t)P::mod(w) : 0;
+    if (w + 1 < N) x |= (uint64_t)P::mod(w + 1) << 32;
+    return (int32_t)((x >> s) & 0x3fffffffu);
+  }
+  ZKB_HD static Fp inv_safegcd(const Fp& a) {
+    constexpr int32_t M30 = 0x3fffffff;
+    constexpr uint32_t pinv30 = (0u - P::INV) & 0x3fffffffu;          // p^-1 mod 2^30
+    int32_t d[L30], e[L30], f[L30], g[L30];
+#pragma unroll
+    for (int i = 0; i < L30; i++) {
+      const int bit = 30 * i, w = bit >> 5, s = bit & 31;
+      uint64_t x = w < N ? (uint64_t)a.v[w] : 0;
+      if (w + 1 < N) x |= (uint64_t)a.v[w + 1] << 32;
+      g[i] = (int32_t)((x >> s) & 0x3fffffffu);
+      f[i] = mod30(i);
+      d[i] = 0;
+      e[i] = i == 0 ? 1 : 0;
+    }
+    int32_t zeta = -1;                                                // -(delta + 1/2), delta = 1/2
+    for (int batch = 0; batch < kMaxBatches; batch++) {
+      int32_t gz = 0;
+#pragma unroll
+      for (int i = 0; i < L30; i++) gz |= g[i];
+      if (gz == 0) break;
+      // 30 division steps on the low limbs -> t = (u v; q r)
+      uint32_t u = 1, v = 0, q = 0, r = 1, fl = (uint32_t)f[0], gl = (uint32_t)g[0];
+#pragma unroll 6
+      for (int i = 0; i < 30; i++) {
+        uint32_t c1 = (uint32_t)(zeta >> 31);                         // delta > 0
+        const uint32_t c2 = 0u - (gl & 1u);                           // g odd
+        const uint32_t x = (fl ^ c1) - c1, y = (u ^ c1) - c1, z = (v ^ c1) - c1;
+        gl += x & c2; q += y & c2; r += z & c2;
+        c1 &= c2;
+        zeta = (int32_t)((uint32_t)zeta ^ c1) - 1;
+        fl += gl & c1; u += q & c1; v += r & c1;
+        gl >>= 1; u <<= 1; v <<= 1;
+      }
+      const int32_t tu = (int32_t)u, tv = (int32_t)v, tq = (int32_t)q, tr = (int32_t)r;
+      // (d, e) <- t * (d, e) / 2^30 mod p: a multiple of p is added first so the division is exact
+      {
+        const int32_t sd = d[L30 - 1] >> 31, se = e[L30 - 1] >> 31;
+        int32_t md = (tu & sd) + (tv & se), me = (tq & sd) + (tr & se);
+        int64_t cd = (int64_t)tu * d[0] + (int64_t)tv * e[0];
+        int64_t ce = (int64_t)tq * d[0] + (int64_t)tr * e[0];
+        md -= (int32_t)((pinv30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);
+        me -= (int32_t)((pinv30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
+        cd += (int64_t)mod30(0) * md;
+        ce += (int64_t)mod30(0) * me;
+        cd >>= 30;
+        ce >>= 30;
+#pragma unroll
+        for (int i = 1; i < L30; i++) {
+          const int32_t di = d[i], ei = e[i];
+          cd += (int64_t)tu * di + (int64_t)tv * ei + (int64_t)mod30(i) * md;
+          ce += (int64_t)tq * di + (int64_t)tr * ei + (int64_t)mod30(i) * me;
+          d[i - 1] = (int32_t)cd & M30;
+          e[i - 1] = (int32_t)ce & M30;
+          cd >>= 30;
+          ce >>= 30;
+        }
+        d[L30 - 1] = (int32_t)cd;
+        e[L30 - 1] = (int32_t)ce;
+      }
+      // (f, g) <- t * (f, g) / 2^30 (exact)
+      {
+        int64_t cf = (int64_t)tu * f[0] + (int64_t)tv * g[0];
+        int64_t cg = (int64_t)tq * f[0] + (int64_t)tr * g[0];
+        cf >>= 30;
+        cg >>= 30;
+#pragma unroll
+        for (int i = 1; i < L30; i++) {
+          const int32_t fi = f[i], gi = g[i];
+          cf += (int64_t)tu * fi + (int64_t)tv * gi;
+          cg += (int64_t)tq * fi + (int64_t)tr * gi;
+          f[i - 1] = (int32_t)cf & M30;
+          g[i - 1] = (int32_t)cg & M30;
+          cf >>= 30;
+          cg >>= 30;
+        }
+        f[L30 - 1] = (int32_t)cf;
+        g[L30 - 1] = (int32_t)cg;
+      }
+    }
+    // f = +-1 (or +-p when a == 0, then d == 0 mod p): x^-1 = d * sign(f), brought into [0, p)
+    {
+      const int32_t sign = f[L30 - 1] >> 31;                          // all ones when f < 0
+      int32_t cond_add = d[L30 - 1] >> 31;
+#pragma unroll
+      for (int i = 0; i < L30; i++) d[i] = ((d[i] + (mod30(i) & cond_add)) ^ sign) - sign;
+#pragma unroll
+      for (int i = 0; i < L30 - 1; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+      cond_add = d[L30 - 1] >> 31;
+#pragma unroll
+      for (int i = 0; i < L30; i++) d[i] += mod30(i) & cond_add;
+#pragma unroll
+      for (int i = 0; i < L30 - 1; i++) { d[i + 1] += d[i] >> 30; d[i] &= M30; }
+    }
+    Fp rr;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      const int bit = 32 * j, k = bit / 30, o = bit - 30 * k;
+      uint64_t x = (uint64_t)(uint32_t)d[k] >> o;
+      if (k + 1 < L30) x |= (uint64_t)(uint32_t)d[k + 1] << (30 - o);
+      if (k + 2 < L30) x |= (uint64_t)(uint32_t)d[k + 2] << (60 - o);
+      rr.v[j] = (uint32_t)x;
+    }
+    // rr = (a R)^-1 = a^-1 R^-1 -> a^-1 R
+    return mul(mul(rr, r2()), r2());
+  }
+
+  ZKB_HD static Fp inv_fast(const Fp& a) { return inv_safegcd(a); }
+
   // a^e for a runtime 64-bit exponent
   ZKB_HD static Fp pow_u64(const Fp& a, uint64_t e) {
     Fp r = one();
@@ -412,6 +537,14 @@ template <class P>
 inline Fp<P> fp_mul_call(Fp<P> a, Fp<P> b) { return Fp<P>::mul(a, b); }
 #endif
 
+#ifdef __CUDACC__
+template <class P>
+__device__ __noinline__ Fp<P> fp_inv_safegcd_call(Fp<P> a) { return Fp<P>::inv_safegcd(a); }
+#else
+template <class P>
+inline Fp<P> fp_inv_safegcd_call(Fp<P> a) { return Fp<P>::inv_safegcd(a); }
+#endif
+
 template <class P>
 struct alignas(16) FpC {
   static constexpr int N = P::N;
@@ -429,6 +562,7 @@ struct alignas(16) FpC {
   ZKB_HD static FpC mul(const FpC& a, const FpC& b) { return {fp_mul_call<P>(a.f, b.f)}; }
   ZKB_HD static FpC sqr(const FpC& a) { return {fp_mul_call<P>(a.f, a.f)}; }
   ZKB_HD static FpC inv(const FpC& a) { return {Fp<P>::inv(a.f)}; }
+  ZKB_HD static FpC inv_fast(const FpC& a) { return {fp_inv_safegcd_call<P>(a.f)}; }
 };
 
 template <class P, class BaseT = Fp<P>>
@@ -461,6 +595,10 @@ struct Fp2 {
   }
   ZKB_HD static Fp2 inv(const Fp2& a) {
     Base n = Base::inv(Base::add(Base::sqr(a.c0), Base::sqr(a.c1)));
+    return {Base::mul(a.c0, n), Base::neg(Base::mul(a.c1, n))};
+  }
+  ZKB_HD static Fp2 inv_fast(const Fp2& a) {
+    Base n = Base::inv_fast(Base::add(Base::sqr(a.c0), Base::sqr(a.c1)));
     return {Base::mul(a.c0, n), Base::neg(Base::mul(a.c1, n))};
   }
 };

@@ -211,11 +211,19 @@ struct MsmSched {
   uint32_t n_chunks;      // total chunk blocks of the big buckets
   uint32_t pad;
 };
+}  // namespace zkb
+#include "msm_batch.cuh"
+namespace zkb {
+
 // A bucket is "big" when one thread adding it sequentially would stretch the kernel's critical path:
 // a lone warp retires a mixed addition in ~7 us, the whole grid ~2.6 G of them per second, so a bucket
 // may hold up to ~entries / 32768 entries before it is worth cutting it into chunks.
-inline uint32_t msm_big_threshold(size_t max_entries) {
+// With few buckets (small c) the AVERAGE list is already that long; only lists well above the average are outliers
+// (a 2^19-point G2 MSM at c = 16 sent half of its entries through the chunk path: 27 of 43 ms).
+inline uint32_t msm_big_threshold(size_t max_entries, uint32_t n_buckets) {
   size_t t = max_entries >> 15;
+  const size_t avg4 = 4 * (max_entries / (n_buckets ? n_buckets : 1) + 1);
+  if (t < avg4) t = avg4;
   if (t < (size_t)kMinBigBucket) t = kMinBigBucket;
   if (t > (size_t)kSizeBins) t = kSizeBins;
   return (uint32_t)t;
@@ -554,6 +562,13 @@ inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
   return best_c;
 }
 
+// Batched-affine bucket accumulation (msm_batch.cuh) instead of the XYZZ loop.  ZKB_MSM_BATCH=0/1 overrides (read per
+// call: the parity tests run both).
+inline bool msm_batch_affine() {
+  const char* e = getenv("ZKB_MSM_BATCH");
+  return e ? atoi(e) != 0 : true;
+}
+
 // Pair levels before the XYZZ accumulation: each level moves half of the remaining additions to the
 // cheaper batched-affine form but costs a scan and a kernel of its own, so stop when the lists are short
 // (average load: entries per bucket).  ZKB_MSM_PAIR_LEVELS overrides (0 = XYZZ only).
@@ -728,7 +743,7 @@ struct MsmEngine {
     // schedule: regular buckets by decreasing size, big buckets in chunks
     uint32_t *size_hist, *order, *big_list, *big_chunk_off, *chunk_slot;
     MsmSched* sched;
-    const uint32_t big = msm_big_threshold(acc_max);
+    const uint32_t big = msm_big_threshold(acc_max, n_buckets);
     const uint32_t max_big = (uint32_t)(acc_max / (big + 1)) + 1;
     const uint32_t max_chunks = (uint32_t)(acc_max / kChunk) + max_big;
     ZKB_TRY(ws.alloc(&size_hist, (size_t)kSizeBins + 4));       // bins followed by the MsmSched block
@@ -753,6 +768,9 @@ struct MsmEngine {
     ZKB_TRY(ws.alloc(&bucket_acc, n_buckets));
     ZKB_TRY(ws.alloc(&partial, max_chunks));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
+    const bool batch_affine = levels == 0 && msm_batch_affine();
+    Aff* run_acc = nullptr;                     // running affine sums of the batched-affine accumulation, by sorted position
+    if (batch_affine) ZKB_TRY(ws.alloc(&run_acc, n_buckets));
     // the accumulation kernel fills the machine: it goes to the low-priority bulk stream (common.cuh)
     ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
       using FC = typename CallVariant<F>::type;
@@ -762,7 +780,14 @@ struct MsmEngine {
       static const int use_call = []() { const char* e = getenv("ZKB_ACC_CALL"); return e ? atoi(e) : 0; }();
       static const int occ4 = []() { const char* e = getenv("ZKB_ACC_OCC4"); return e ? atoi(e) : 0; }();
       prof_begin(ctx, bs);
-      if (direct)
+      if (batch_affine) {
+        // batched-affine accumulation (msm_batch.cuh): 6 instead of 10 multiplications per entry
+        constexpr unsigned per_block = kBatchThreads * BatchGeom<FC>::G;
+        ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_accumulate_batch<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)BatchGeom<FC>::kSmem));
+        ZKB_LAUNCH(ctx, (k_accumulate_batch<FC>), ceil_div(n_buckets, per_block), kBatchThreads, BatchGeom<FC>::kSmem, bs,
+                   entries, offsets, order, sched, (const Affine<FC>*)srs->table, (Affine<FC>*)run_acc, (XYZZ<FC>*)bucket_acc);
+      } else if (direct)
         ZKB_LAUNCH(ctx, (k_accumulate<F, 1, true>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)nullptr, acc_off,
                    order, sched, acc_pts, bucket_acc);
       else if (use_call)

@@ -22,6 +22,7 @@ template <class F> static void fp_op(int op, const uint32_t* a, const uint32_t* 
     case 6: r = F::sqr(x); break;
     case 7: r = F::neg(x); break;
     case 8: r = F::mul_sos(x, y); break;
+    case 9: r = F::inv_safegcd(x); break;
     default: r = F::zero();
   }
   memcpy(out, &r, sizeof(F));

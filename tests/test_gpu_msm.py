@@ -198,3 +198,34 @@ def test_msm_pair_levels_forced(ctx, cid, group, levels, monkeypatch):
     sc = [rng.randrange(r) if rng.random() < 0.8 else rng.randrange(3) for _ in range(n)]
     want = c.to_affine(msm_pippenger(c, pts, sc, FR[cid].bits))
     assert gpu_msm(ctx, cid, group, pts, sc, True) == want
+
+
+@pytest.mark.parametrize("batch", ["0", "1"])
+@pytest.mark.parametrize("cid,group", [(BN254, 1), (BN254, 2), (BLS12_381, 1), (BLS12_381, 2)])
+def test_msm_batched_affine_forced(ctx, cid, group, batch, monkeypatch):
+    """The batched-affine bucket accumulation (csrc/msm_batch.cuh, ZKB_MSM_BATCH=1) against the XYZZ loop (=0) and the
+    oracle, on inputs that hit every special case of an affine running sum: the same base many times with the same
+    scalar (round 1 is a doubling, later rounds generic), P then -P (the running sum becomes the identity and the next
+    entry has to restart it), identity bases, lists of very different lengths inside one thread, empty buckets."""
+    monkeypatch.setenv("ZKB_MSM_BATCH", batch)
+    c = CURVES[(cid, group)]
+    r = c.r
+    rng = random.Random(int(batch) * 10 + group + 100 * cid)
+    base = H.multiples(cid, group, 40, start=5)
+    k = rng.randrange(r)
+    pts, sc = [], []
+    pts += [base[0]] * 9;                                      sc += [k] * 9              # doubling, then generic additions
+    pts += [base[1], c.neg_affine(base[1])] * 4 + [base[1]];   sc += [k] * 9              # identity running sums that restart
+    pts += [base[2], c.neg_affine(base[2])];                   sc += [k] * 2              # a list that ends as the identity
+    pts += [None, base[3], None];                              sc += [k, k, 5]            # identity bases
+    pts += base[4:];                                           sc += [rng.randrange(r) for _ in base[4:]]
+    pts += base[4:30];                                         sc += [1] * 26             # one heavily loaded bucket
+    want = c.to_affine(msm_naive(c, pts, sc))
+    assert gpu_msm(ctx, cid, group, pts, sc, True) == want
+    assert gpu_msm(ctx, cid, group, pts, sc, False) == want
+    # more lists than one warp owns, against the Pippenger restatement
+    n = 3000 if group == 1 else 700
+    pts = H.multiples(cid, group, n, start=1234)
+    sc = [rng.randrange(r) if rng.random() < 0.8 else rng.randrange(3) for _ in range(n)]
+    want = c.to_affine(msm_pippenger(c, pts, sc, FR[cid].bits))
+    assert gpu_msm(ctx, cid, group, pts, sc, True) == want

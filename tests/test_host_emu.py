@@ -51,6 +51,11 @@ def test_field_ops(lib, fid):
     for a in vals + [1 << k for k in range(0, bits - 1, 37)] + [p - (1 << k) for k in range(0, bits - 1, 41)]:
         a %= p
         assert run(3, a * R % p) == (pow(a, -1, p) * R % p if a else 0)
+        # the division-step inversion (safegcd, 30 steps per batch) has the same contract
+        assert run(9, a * R % p) == (pow(a, -1, p) * R % p if a else 0)
+    for _ in range(3000):
+        a = rng.randrange(1, p)
+        assert run(9, a) == pow(a * Rinv % p, -1, p) * R % p
 
 
 @pytest.mark.parametrize("cid", [BN254, BLS12_381])

@@ -21,6 +21,7 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--levels", type=int, nargs="*", default=[0, 1, 2, 3])
 ap.add_argument("--scales", type=int, nargs="*", default=[0, 1, 2, 4])
 ap.add_argument("--groups", type=int, nargs="*", default=[1, 2])
+ap.add_argument("--batch", type=int, nargs="*", default=[0], help="ZKB_MSM_BATCH values (batched-affine accumulation, msm_batch.cuh)")
 a = ap.parse_args()
 ctx = Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream)
@@ -36,8 +37,9 @@ for group in a.groups:
     srs = ctx.srs_upload(1, group, np.concatenate(xs), np.concatenate(infs))
     d = torch.from_numpy(synth.random_scalars(rng, n, 1).view(np.int64)).cuda()
     base = None
-    for lv in a.levels:
+    for lv, bt in [(lv, bt) for bt in a.batch for lv in a.levels]:
         for sc in (a.scales if lv else [0]):
+            os.environ["ZKB_MSM_BATCH"] = str(bt)
             os.environ["ZKB_MSM_PAIR_LEVELS"] = str(lv)
             os.environ["ZKB_PAIR_SCALE"] = str(sc)
             for _ in range(2):
@@ -56,7 +58,7 @@ for group in a.groups:
                     en[i].record()
             torch.cuda.synchronize()
             ms = sorted(x.elapsed_time(y) for x, y in zip(st, en))
-            print(json.dumps({"group": group, "log_n": n.bit_length() - 1, "pair_levels": lv, "pair_scale": sc,
+            print(json.dumps({"group": group, "log_n": n.bit_length() - 1, "batch_affine": bt, "pair_levels": lv, "pair_scale": sc,
                               "ms_median": ms[len(ms) // 2], "ms_min": ms[0], "same_result_as_levels0": same}), flush=True)
     srs.free()
     del d
