@@ -565,8 +565,11 @@ inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
 // Batched-affine bucket accumulation (msm_batch.cuh) instead of the XYZZ loop.  ZKB_MSM_BATCH=0/1 overrides (read per
 // call: the parity tests run both).
 inline bool msm_batch_affine() {
+  // Default off: measured on B200 (2^20 BLS12-381 G1) 13.6 ms against 6.0 ms for the XYZZ loop -- with one list per
+  // slot the 2^19 lists of unequal length (Poisson, mean 26, max ~55) leave the one-wave grid half empty towards the
+  // end, and G = 12 additions per inversion make the inversion as expensive as the additions.
   const char* e = getenv("ZKB_MSM_BATCH");
-  return e ? atoi(e) != 0 : true;
+  return e ? atoi(e) != 0 : false;
 }
 
 // Pair levels before the XYZZ accumulation: each level moves half of the remaining additions to the
@@ -768,31 +771,63 @@ struct MsmEngine {
     ZKB_TRY(ws.alloc(&bucket_acc, n_buckets));
     ZKB_TRY(ws.alloc(&partial, max_chunks));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
+    // batched-affine accumulation (msm_batch.cuh): cut the regular lists into chains of <= lmax entries, one resident wave
     const bool batch_affine = levels == 0 && msm_batch_affine();
-    Aff* run_acc = nullptr;                     // running affine sums of the batched-affine accumulation, by sorted position
-    if (batch_affine) ZKB_TRY(ws.alloc(&run_acc, n_buckets));
+    uint32_t *seg_off = nullptr, *chain_bucket = nullptr;
+    Aff* chain_sum = nullptr;
+    F* chain_prefix = nullptr;
+    unsigned batch_blocks = 0;
+    if (batch_affine) {
+      using FC = typename CallVariant<F>::type;
+      const int bps_env = []() { const char* e = getenv("ZKB_BATCH_BPS"); return e ? atoi(e) : 0; }();
+      const int lmax_env = []() { const char* e = getenv("ZKB_BATCH_LMAX"); return e ? atoi(e) : 0; }();
+      int occ = 0;
+      ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_accumulate_chains<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kBatchSmem));
+      ZKB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_accumulate_chains<FC>, kBatchThreads,
+                                                                  kBatchSmem));
+      int bps = bps_env > 0 ? bps_env : 4;                  // 8 warps per SM keep the multiplier pipe > 90 % busy (chains.cu)
+      if (bps > occ) bps = occ;
+      if (bps < 1) bps = 1;
+      batch_blocks = (unsigned)(ctx->sm_count * bps);
+      const size_t lanes = (size_t)batch_blocks * kBatchThreads;
+      size_t lmax = lmax_env > 0 ? (size_t)lmax_env : (acc_max + lanes * 32 - 1) / (lanes * 32);   // ~32 chains per lane
+      if (lmax_env <= 0) lmax = lmax < 8 ? 8 : lmax > 16 ? 16 : lmax;
+      if (lmax < 2) lmax = 2;
+      const size_t max_chains = acc_max / lmax + n_buckets + 1;
+      ZKB_TRY(ws.alloc(&seg_off, (size_t)n_buckets + 1));
+      ZKB_TRY(ws.alloc(&chain_bucket, max_chains));
+      ZKB_TRY(ws.alloc(&chain_sum, max_chains));
+      ZKB_TRY(ws.alloc(&chain_prefix, lanes * kBatchMaxG));
+      ZKB_LAUNCH(ctx, k_chain_count, ceil_div(n_buckets, 256), 256, 0, st, acc_off, n_buckets, big, (uint32_t)lmax, seg_off);
+      ZKB_LAUNCH(ctx, k_scan_tiles, n_tiles, kScanThreads, 0, st, seg_off, n_buckets, tile_sums);
+      ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, tile_sums, n_tiles);
+      ZKB_LAUNCH(ctx, k_scan_finish, ceil_div(n_buckets, 256), 256, 0, st, seg_off, n_buckets, tile_sums, n_tiles,
+                 (uint32_t*)nullptr);
+      ZKB_LAUNCH(ctx, k_chain_build, ceil_div(n_buckets, 256), 256, 0, st, (const uint32_t*)seg_off, n_buckets, chain_bucket);
+    }
     // the accumulation kernel fills the machine: it goes to the low-priority bulk stream (common.cuh)
     ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
       using FC = typename CallVariant<F>::type;
       static_assert(sizeof(Affine<FC>) == sizeof(Aff) && sizeof(XYZZ<FC>) == sizeof(Pt), "call variant layout");
       // tuning switches (defaults chosen from measurements): multiplication as a call,
       // and a register cap that trades a few spills for a fourth resident block per SM
-      static const int use_call = []() { const char* e = getenv("ZKB_ACC_CALL"); return e ? atoi(e) : 0; }();
+      const int use_call = []() { const char* e = getenv("ZKB_ACC_CALL"); return e ? atoi(e) : 0; }();
       static const int occ4 = []() { const char* e = getenv("ZKB_ACC_OCC4"); return e ? atoi(e) : 0; }();
       prof_begin(ctx, bs);
       if (batch_affine) {
-        // batched-affine accumulation (msm_batch.cuh): 6 instead of 10 multiplications per entry
-        constexpr unsigned per_block = kBatchThreads * BatchGeom<FC>::G;
-        ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_accumulate_batch<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)BatchGeom<FC>::kSmem));
-        ZKB_LAUNCH(ctx, (k_accumulate_batch<FC>), ceil_div(n_buckets, per_block), kBatchThreads, BatchGeom<FC>::kSmem, bs,
-                   entries, offsets, order, sched, (const Affine<FC>*)srs->table, (Affine<FC>*)run_acc, (XYZZ<FC>*)bucket_acc);
+        // batched-affine accumulation over equal-length chains (msm_batch.cuh): 6 instead of 10 multiplications per entry
+        ZKB_LAUNCH(ctx, (k_accumulate_chains<FC>), batch_blocks, kBatchThreads, kBatchSmem, bs, entries, offsets,
+                   (const uint32_t*)seg_off, (const uint32_t*)chain_bucket, n_buckets, (const Affine<FC>*)srs->table,
+                   (Affine<FC>*)chain_sum, (FC*)chain_prefix);
+        ZKB_LAUNCH(ctx, (k_chain_combine<FC>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)seg_off, n_buckets,
+                   (const Affine<FC>*)chain_sum, (XYZZ<FC>*)bucket_acc);
       } else if (direct)
         ZKB_LAUNCH(ctx, (k_accumulate<F, 1, true>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)nullptr, acc_off,
                    order, sched, acc_pts, bucket_acc);
-      else if (use_call)
-        ZKB_LAUNCH(ctx, (k_accumulate<FC, 3>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets, order, sched,
-                   (const Affine<FC>*)srs->table, (XYZZ<FC>*)bucket_acc);
+      else if (use_call & (sizeof(F) <= 48 ? 1 : 2))      // bit 0: G1, bit 1: G2
+        ZKB_LAUNCH(ctx, (k_accumulate<FC, (sizeof(F) <= 48 ? 3 : 2)>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets,
+                   order, sched, (const Affine<FC>*)srs->table, (XYZZ<FC>*)bucket_acc);
       else if (occ4)
         ZKB_LAUNCH(ctx, (k_accumulate<F, 4>), ceil_div(n_buckets, 128), 128, 0, bs, entries, offsets, order, sched,
                    (const Aff*)srs->table, bucket_acc);
