@@ -82,6 +82,7 @@ SIGNATURES = {
     "zkb_groth16_prove_partial": (c_int, [c_void_p, c_void_p, ctypes.POINTER(Csr), ctypes.POINTER(Csr), ctypes.POINTER(Csr),
                                           c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "zkb_groth16_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "zkb_msm_batch": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "zkb_fixed_base_mul": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "zkb_points_decompress": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_uint, c_void_p, c_void_p, c_void_p]),
     "zkb_fr_convert": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int]),

@@ -194,6 +194,25 @@ class Context:
         self._check(fn(self.handle, srs.handle, base_offset, _addr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
         return out, bool(oinf[0])
 
+    def msm_batch(self, srs_list, scalars_list, base_offsets=None, mont=False):
+        """k independent MSMs in one call (zkb_msm_batch): [(xy, is_identity)] in order.  scalars: host or device arrays"""
+        k = len(srs_list)
+        if k == 0:
+            return []
+        if len(scalars_list) != k:
+            raise ValueError("one scalar array per SRS")
+        base_offsets = [0] * k if base_offsets is None else list(base_offsets)
+        sc = [_fr(s) for s in scalars_list]
+        w = point_words(srs_list[0].curve, srs_list[0].group)
+        handles = (ctypes.c_void_p * k)(*[s.handle for s in srs_list])
+        offs = (ctypes.c_size_t * k)(*base_offsets)
+        ptrs = (ctypes.c_void_p * k)(*[(a.data_ptr() if is_dev(a) else a.ctypes.data) if a.shape[0] else None for a in sc])
+        lens = (ctypes.c_size_t * k)(*[a.shape[0] for a in sc])
+        out = np.zeros((k, w), dtype=np.uint64)
+        oinf = np.zeros(k, dtype=np.uint8)
+        self._check(self.lib.zkb_msm_batch(self.handle, k, handles, offs, ptrs, lens, 1 if mont else 0, _ptr(out), _ptr(oinf)))
+        return [(out[i], bool(oinf[i])) for i in range(k)]
+
     def msm_dev(self, srs, d_scalars_ptr, n, base_offset=0):
         """Same with canonical scalars already in device memory (raw device pointer)."""
         out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)

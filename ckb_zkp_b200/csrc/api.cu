@@ -249,6 +249,50 @@ int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void
       ->msm_to_host(ctx, srs, base_offset, (const uint32_t*)d_scalars_canonical, n, 0, out_xy, out_inf);
 }
 
+// k MSMs on the side streams, one conversion + copy of the k results at the end
+int zkb_msm_batch(zkb_ctx* ctx, size_t k, const zkb_srs* const* srs, const size_t* base_offsets,
+                  const uint64_t* const* scalars, const size_t* n, int scalars_mont, uint64_t* out_xy, uint8_t* out_inf) {
+  if (!ctx || (k && (!srs || !base_offsets || !scalars || !n || !out_xy || !out_inf))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (k == 0) return ZKB_OK;
+  if (k > 4096) return set_err(ctx, ZKB_E_INVALID, "msm_batch: too many MSMs in one call");
+  for (size_t i = 0; i < k; i++) {
+    if (!srs[i] || (n[i] && !scalars[i])) return set_err(ctx, ZKB_E_INVALID, "msm_batch: null argument for MSM %zu", i);
+    if (srs[i]->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm_batch: srs belongs to another context");
+    if (srs[i]->curve != srs[0]->curve || srs[i]->group != srs[0]->group)
+      return set_err(ctx, ZKB_E_INVALID, "msm_batch: all MSMs of one call must share curve and group");
+  }
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  const GroupOps* ops = group_ops(srs[0]->curve, srs[0]->group);
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint8_t *d_pts, *d_aff, *d_inf;
+  ZKB_TRY(ws.alloc(&d_pts, k * ops->xyzz_bytes));
+  ZKB_TRY(ws.alloc(&d_aff, k * ops->affine_bytes));
+  ZKB_TRY(ws.alloc(&d_inf, k));
+  // scalar copies on the main stream (stream-ordered scratch), the MSMs fan out over the side streams
+  std::vector<uint32_t*> d_sc(k, nullptr);
+  std::vector<size_t> len(k, 0);
+  for (size_t i = 0; i < k; i++) {
+    size_t avail = base_offsets[i] <= srs[i]->n ? srs[i]->n - base_offsets[i] : 0;
+    len[i] = n[i] < avail ? n[i] : avail;
+    ZKB_TRY(ws.alloc(&d_sc[i], len[i] * 8));
+    if (len[i]) ZKB_CUDA(ctx, cudaMemcpyAsync(d_sc[i], scalars[i], len[i] * 32, cudaMemcpyDefault, st));
+  }
+  const int lanes = ctx->serial ? 0 : kNumSideStreams;
+  if (lanes) ZKB_TRY(fork_streams(ctx, lanes));
+  for (size_t i = 0; i < k; i++) {
+    cudaStream_t s_i = lanes ? ctx->side[i % lanes] : st;
+    ZKB_TRY(ops->msm_run(ctx, s_i, srs[i], base_offsets[i], d_sc[i], len[i], scalars_mont, d_pts + i * ops->xyzz_bytes));
+  }
+  if (lanes) ZKB_TRY(join_streams(ctx, lanes));
+  ZKB_TRY(ops->to_affine(ctx, st, d_pts, k, d_aff, d_inf));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy, d_aff, k * ops->affine_bytes, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, k, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 // ---- sharded MSM (one process per GPU) ---------------------------------------------------------
 // This rank's partial of multi_scalar_mul(&bases[base_offset .. base_offset + n), &scalars[..n)) over the LOGICAL
 // SRS: the pairs whose base lies in this rank's shard [global_lo, global_lo + srs->n).  `scalars` points at the full

@@ -80,9 +80,14 @@ struct GroupImpl {
                d_inf, d_status);
     return ZKB_OK;
   }
+  static int to_affine(zkb_ctx* ctx, cudaStream_t st, const void* d_points, size_t n, void* d_xy, uint8_t* d_inf) {
+    if (n == 0) return ZKB_OK;
+    ZKB_LAUNCH(ctx, (k_to_affine<F>), ceil_div(n, 32), 32, 0, st, (const XYZZ<F>*)d_points, (uint32_t)n, (Affine<F>*)d_xy, d_inf);
+    return ZKB_OK;
+  }
   static const GroupOps* ops() {
     static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host,
-                               &fixed_base_mul, &fold, &decompress};
+                               &fixed_base_mul, &fold, &decompress, &to_affine};
     return &o;
   }
 };

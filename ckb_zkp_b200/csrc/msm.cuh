@@ -619,6 +619,12 @@ struct MsmEngine {
     size_t n_eff = 0;                    // identity bases never produce bucket entries
     for (size_t i = 0; i < n; i++) n_eff += h_inf[i] ? 0 : 1;
     srs->c = msm_pick_c(n_eff, srs->precomp, FrP::BITS);
+    if (srs->precomp && sizeof(F) > sizeof(Fp<typename F::Params>)) {          // G2 (Fq2 coordinates): its own override
+      if (const char* e = getenv("ZKB_MSM_C_G2")) {
+        int v = atoi(e);
+        if (v >= 2 && v <= 23) srs->c = v;
+      }
+    }
     srs->W = msm_windows(FrP::BITS, srs->c);
     if (srs->precomp && (size_t)srs->W * n >= (size_t(1) << 31))
       return set_err(ctx, ZKB_E_INVALID, "precomputed table too large for 31-bit indices");
@@ -771,40 +777,50 @@ struct MsmEngine {
     ZKB_TRY(ws.alloc(&bucket_acc, n_buckets));
     ZKB_TRY(ws.alloc(&partial, max_chunks));
     ZKB_CUDA(ctx, cudaMemsetAsync(bucket_acc, 0, sizeof(Pt) * (size_t)n_buckets, st));     // empty buckets = identity
-    // batched-affine accumulation (msm_batch.cuh): cut the regular lists into chains of <= lmax entries, one resident wave
+    // batched-affine accumulation (msm_batch.cuh): two levels of equal-length chains, then the XYZZ combine
     const bool batch_affine = levels == 0 && msm_batch_affine();
-    uint32_t *seg_off = nullptr, *chain_bucket = nullptr;
-    Aff* chain_sum = nullptr;
+    uint32_t *seg_off0 = nullptr, *seg_off1 = nullptr;
+    uint2 *rec0 = nullptr, *rec1 = nullptr;
+    Aff *chain_sum0 = nullptr, *chain_sum1 = nullptr;
     F* chain_prefix = nullptr;
     unsigned batch_blocks = 0;
     if (batch_affine) {
       using FC = typename CallVariant<F>::type;
-      const int bps_env = []() { const char* e = getenv("ZKB_BATCH_BPS"); return e ? atoi(e) : 0; }();
-      const int lmax_env = []() { const char* e = getenv("ZKB_BATCH_LMAX"); return e ? atoi(e) : 0; }();
+      auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
       int occ = 0;
-      ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_accumulate_chains<FC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kBatchSmem));
-      ZKB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_accumulate_chains<FC>, kBatchThreads,
-                                                                  kBatchSmem));
-      int bps = bps_env > 0 ? bps_env : 4;                  // 8 warps per SM keep the multiplier pipe > 90 % busy (chains.cu)
+      ZKB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_accumulate_chains<FC, true>,
+                                                                  kBatchThreads, 0));
+      int bps = env_int("ZKB_BATCH_BPS", 4);                // 8 warps per SM keep the multiplier pipe > 90 % busy (chains.cu)
       if (bps > occ) bps = occ;
       if (bps < 1) bps = 1;
       batch_blocks = (unsigned)(ctx->sm_count * bps);
       const size_t lanes = (size_t)batch_blocks * kBatchThreads;
-      size_t lmax = lmax_env > 0 ? (size_t)lmax_env : (acc_max + lanes * 32 - 1) / (lanes * 32);   // ~32 chains per lane
-      if (lmax_env <= 0) lmax = lmax < 8 ? 8 : lmax > 16 ? 16 : lmax;
-      if (lmax < 2) lmax = 2;
-      const size_t max_chains = acc_max / lmax + n_buckets + 1;
-      ZKB_TRY(ws.alloc(&seg_off, (size_t)n_buckets + 1));
-      ZKB_TRY(ws.alloc(&chain_bucket, max_chains));
-      ZKB_TRY(ws.alloc(&chain_sum, max_chains));
-      ZKB_TRY(ws.alloc(&chain_prefix, lanes * kBatchMaxG));
-      ZKB_LAUNCH(ctx, k_chain_count, ceil_div(n_buckets, 256), 256, 0, st, acc_off, n_buckets, big, (uint32_t)lmax, seg_off);
-      ZKB_LAUNCH(ctx, k_scan_tiles, n_tiles, kScanThreads, 0, st, seg_off, n_buckets, tile_sums);
-      ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, tile_sums, n_tiles);
-      ZKB_LAUNCH(ctx, k_scan_finish, ceil_div(n_buckets, 256), 256, 0, st, seg_off, n_buckets, tile_sums, n_tiles,
-                 (uint32_t*)nullptr);
-      ZKB_LAUNCH(ctx, k_chain_build, ceil_div(n_buckets, 256), 256, 0, st, (const uint32_t*)seg_off, n_buckets, chain_bucket);
+      int l0 = env_int("ZKB_BATCH_L0", 8), l1 = env_int("ZKB_BATCH_L1", 8);
+      if (l0 < 2) l0 = 2;
+      if (l1 < 2) l1 = 2;
+      const size_t max_chains0 = acc_max / (size_t)l0 + n_buckets + 1, max_chains1 = max_chains0 / (size_t)l1 + n_buckets + 1;
+      ZKB_TRY(ws.alloc(&seg_off0, (size_t)n_buckets + 1));
+      ZKB_TRY(ws.alloc(&seg_off1, (size_t)n_buckets + 1));
+      ZKB_TRY(ws.alloc(&rec0, max_chains0));
+      ZKB_TRY(ws.alloc(&rec1, max_chains1));
+      ZKB_TRY(ws.alloc(&chain_sum0, max_chains0));
+      ZKB_TRY(ws.alloc(&chain_sum1, max_chains1));
+      ZKB_TRY(ws.alloc(&chain_prefix, lanes * kBatchGMax));
+      // the chain structure of both levels depends on the list lengths only: built before the accumulation starts
+      const uint32_t* lists = acc_off;
+      uint32_t* seg[2] = {seg_off0, seg_off1};
+      uint2* recs[2] = {rec0, rec1};
+      for (int lvl = 0; lvl < 2; lvl++) {
+        ZKB_LAUNCH(ctx, k_chain_count, ceil_div(n_buckets, 256), 256, 0, st, lists, n_buckets, lvl == 0 ? big : 0xffffffffu,
+                   (uint32_t)(lvl == 0 ? l0 : l1), seg[lvl]);
+        ZKB_LAUNCH(ctx, k_scan_tiles, n_tiles, kScanThreads, 0, st, seg[lvl], n_buckets, tile_sums);
+        ZKB_LAUNCH(ctx, k_scan_sums, 1, 1024, 0, st, tile_sums, n_tiles);
+        ZKB_LAUNCH(ctx, k_scan_finish, ceil_div(n_buckets, 256), 256, 0, st, seg[lvl], n_buckets, tile_sums, n_tiles,
+                   (uint32_t*)nullptr);
+        ZKB_LAUNCH(ctx, k_chain_build, ceil_div(n_buckets, 256), 256, 0, st, lists, (const uint32_t*)seg[lvl], n_buckets,
+                   recs[lvl]);
+        lists = seg[lvl];
+      }
     }
     // the accumulation kernel fills the machine: it goes to the low-priority bulk stream (common.cuh)
     ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
@@ -816,12 +832,15 @@ struct MsmEngine {
       static const int occ4 = []() { const char* e = getenv("ZKB_ACC_OCC4"); return e ? atoi(e) : 0; }();
       prof_begin(ctx, bs);
       if (batch_affine) {
-        // batched-affine accumulation over equal-length chains (msm_batch.cuh): 6 instead of 10 multiplications per entry
-        ZKB_LAUNCH(ctx, (k_accumulate_chains<FC>), batch_blocks, kBatchThreads, kBatchSmem, bs, entries, offsets,
-                   (const uint32_t*)seg_off, (const uint32_t*)chain_bucket, n_buckets, (const Affine<FC>*)srs->table,
-                   (Affine<FC>*)chain_sum, (FC*)chain_prefix);
-        ZKB_LAUNCH(ctx, (k_chain_combine<FC>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)seg_off, n_buckets,
-                   (const Affine<FC>*)chain_sum, (XYZZ<FC>*)bucket_acc);
+        // 6 instead of 10 multiplications per entry: level 0 gathers from the table, level 1 sums the chain sums
+        ZKB_LAUNCH(ctx, (k_accumulate_chains<FC, true>), batch_blocks, kBatchThreads, 0, bs, entries,
+                   (const Affine<FC>*)srs->table, (const uint2*)rec0, (const uint32_t*)(seg_off0 + n_buckets),
+                   (Affine<FC>*)chain_sum0, (FC*)chain_prefix, kBatchGMax);
+        ZKB_LAUNCH(ctx, (k_accumulate_chains<FC, false>), batch_blocks, kBatchThreads, 0, bs, (const uint32_t*)nullptr,
+                   (const Affine<FC>*)chain_sum0, (const uint2*)rec1, (const uint32_t*)(seg_off1 + n_buckets),
+                   (Affine<FC>*)chain_sum1, (FC*)chain_prefix, kBatchGMax);
+        ZKB_LAUNCH(ctx, (k_chain_combine<FC>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)seg_off1, n_buckets,
+                   (const Affine<FC>*)chain_sum1, (XYZZ<FC>*)bucket_acc);
       } else if (direct)
         ZKB_LAUNCH(ctx, (k_accumulate<F, 1, true>), ceil_div(n_buckets, 128), 128, 0, bs, (const uint32_t*)nullptr, acc_off,
                    order, sched, acc_pts, bucket_acc);
@@ -874,7 +893,11 @@ struct MsmEngine {
       Pt* bufs[2] = {tmp_a, tmp_b};
       int flip = 0;
       while (len > 1) {
-        uint32_t K = len < (uint32_t)kSegK ? len : (uint32_t)kSegK;
+        // 4-way passes while the axis is long (many short waves instead of two long ones: the 8-way first pass was 1.15
+        // waves of 7 dependent additions), one last pass of up to 8
+        const uint32_t k_env = []() { const char* e = getenv("ZKB_SEG_K"); return e ? (uint32_t)atoi(e) : 0u; }();
+        const uint32_t k_pass = k_env >= 2 && k_env <= 16 && !(k_env & (k_env - 1)) ? k_env : 4u;
+        uint32_t K = len <= (uint32_t)kSegK ? len : k_pass;
         uint32_t new_len = len / K;                 // powers of two throughout
         uint32_t n_out = new_len * other;
         Pt* out = new_len == 1 ? final_out : bufs[flip];
@@ -951,6 +974,8 @@ struct GroupOps {
   // ark-serialize compressed points (affine_bytes / 2 bytes each) -> affine Montgomery + identity flags + per-point status
   int (*decompress)(zkb_ctx*, cudaStream_t, const uint8_t* d_in, size_t n, int check_subgroup, void* d_out_affine,
                     uint8_t* d_out_inf, uint8_t* d_out_status);
+  // n XYZZ points -> canonical affine + identity flags
+  int (*to_affine)(zkb_ctx*, cudaStream_t, const void* d_points, size_t n, void* d_out_affine, uint8_t* d_out_inf);
 };
 const GroupOps* group_ops(int curve, int group);
 

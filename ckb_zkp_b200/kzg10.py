@@ -182,8 +182,83 @@ def kzg_open(ck, p, point_mont, rand):
     return w, rand_v
 
 
+def _commit_job(ck, p, hiding_bound, rng, base_offset=0, supported_degree=None):
+    """the checks and rng draws of KZG10::commit (kzg10.rs:100-123) without the MSMs: -> (jobs, Randomness) where jobs
+    is [(srs, base_offset, scalars)] -- the commitment is the sum of the jobs' MSMs"""
+    sup = (ck.n - 1 - base_offset) if supported_degree is None else supported_degree
+    deg = _degree(p)
+    if deg < 1:
+        raise DegreeIsZero()
+    if deg > sup:
+        raise DegreeOutOfBound()
+    nz = _leading_zeros(p)                                       # skip_leading_zeros_and_convert_to_bigints
+    jobs = [(ck.g, base_offset + nz, p[nz:])]
+    rand = Randomness()
+    if hiding_bound is not None:
+        if rng is None:
+            raise MissingRng()
+        if hiding_bound == 0:
+            raise HidingBoundIsZero()
+        if hiding_bound > ck.n - base_offset or hiding_bound + 1 > ck.n_hiding:
+            raise HidingBoundTooLarge()
+        rand = Randomness.rand(ck, hiding_bound, rng)
+        jobs.append((ck.gamma_g, 0, rand.blinding))
+    return jobs, rand
+
+
+def _add_point_groups(ctx, curve, groups):
+    """[[points]] -> [sum of each group] with one upload and one batched call (unit-scalar MSMs over a throw-away SRS)"""
+    flat = [p for g in groups for p in g]
+    xy = np.stack([p[0] for p in flat])
+    inf = np.array([1 if p[1] else 0 for p in flat], dtype=np.uint8)
+    srs = ctx.srs_upload(curve, _lib.G1, xy, inf, precompute=False)
+    try:
+        ones = np.zeros((max(len(g) for g in groups), 4), dtype=np.uint64)
+        ones[:, 0] = 1
+        offs, pos = [], 0
+        for g in groups:
+            offs.append(pos)
+            pos += len(g)
+        return ctx.msm_batch([srs] * len(groups), [ones[:len(g)] for g in groups], offs)
+    finally:
+        srs.free()
+
+
 def pc_commit(ck, polynomials, rng=None):
-    """PC::commit (pc/mod.rs:34-71) -> ([(comm, shifted_comm or None)], [(rand, shifted_rand or None)])"""
+    """PC::commit (pc/mod.rs:34-71) -> ([(comm, shifted_comm or None)], [(rand, shifted_rand or None)]).
+    The reference commits polynomial by polynomial; the rng draws happen in that order here too, while the MSMs of all
+    the commitments of the call go to the device together (zkb_msm_batch: their sorts, accumulations and reductions
+    overlap on the side streams).  With a sharded committer key every MSM is a collective and they run one by one."""
+    if ck.shard is not None:
+        return _pc_commit_serial(ck, polynomials, rng)
+    ctx = ck.ctx
+    jobs, slots, rands = [], [], []            # slots[i] = (job indices of comm, job indices of shifted comm or None)
+    for P in polynomials:
+        j, rand = _commit_job(ck, P.coeffs, P.hiding_bound, rng, supported_degree=ck.supported_degree)
+        main = list(range(len(jobs), len(jobs) + len(j)))
+        jobs += j
+        shifted, shifted_rand = None, None
+        if P.degree_bound is not None:
+            if P.degree_bound > ck.supported_degree:
+                raise DegreeOutOfBound()
+            off = ck.supported_degree - P.degree_bound              # shifted_powers (data_structures.rs:87-99)
+            j, shifted_rand = _commit_job(ck, P.coeffs, P.hiding_bound, rng, base_offset=off, supported_degree=P.degree_bound)
+            shifted = list(range(len(jobs), len(jobs) + len(j)))
+            jobs += j
+        slots.append((main, shifted))
+        rands.append((rand, shifted_rand))
+    pts = ctx.msm_batch([j[0] for j in jobs], [j[2] for j in jobs], [j[1] for j in jobs], mont=True) if jobs else []
+    groups = [idx for pair in slots for idx in pair if idx is not None and len(idx) > 1]
+    sums = iter(_add_point_groups(ctx, ck.curve, [[pts[i] for i in idx] for idx in groups]) if groups else [])
+    value = lambda idx: None if idx is None else (pts[idx[0]] if len(idx) == 1 else next(sums))
+    comms = []
+    for main, shifted in slots:                 # same order as `groups` was built in
+        c = value(main)
+        comms.append((c, value(shifted)))
+    return comms, rands
+
+
+def _pc_commit_serial(ck, polynomials, rng=None):
     comms, rands = [], []
     for P in polynomials:
         comm, rand = kzg_commit(ck, P.coeffs, P.hiding_bound, rng, supported_degree=ck.supported_degree)

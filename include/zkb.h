@@ -106,6 +106,16 @@ int zkb_msm_mont(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const uin
 int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void* d_scalars_canonical,
                 size_t n, uint64_t* out_xy, uint8_t* out_inf);
 
+/* k independent MSMs in one call -- the shape of the reference's commitment loops: PC::commit commits polynomial by
+ * polynomial (marlin/src/pc/mod.rs:42-69), the `Curve::vartime_multiscalar_mul` consumers commit vector by vector
+ * (spartan/src/commitments.rs:42-56, asvc/src/lib.rs:160-225).  MSM i is multi_scalar_mul(&srs[i][base_offsets[i]..],
+ * scalars[i][..n[i]]) (zip semantics); the k sorts, accumulations and bucket reductions run concurrently on the
+ * library's side streams, the k results are converted and fetched together.  scalars[i] may be host or device memory;
+ * scalars_mont selects Montgomery (into_repr fused) or canonical input for all of them.  out_xy: k affine points of
+ * the respective group back to back (all SRS handles of one call must belong to the same curve and group). */
+int zkb_msm_batch(zkb_ctx* ctx, size_t k, const zkb_srs* const* srs, const size_t* base_offsets,
+                  const uint64_t* const* scalars, const size_t* n, int scalars_mont, uint64_t* out_xy, uint8_t* out_inf);
+
 /* ---- radix-2 NTT over Fr --------------------------------------------------------------------
  * EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place of ark-poly 0.2 as used in
  * groth16/src/r1cs_to_qap.rs:144-169: natural order in and out, 2^log_n elements of 4 limbs

@@ -229,3 +229,29 @@ def test_msm_batched_affine_forced(ctx, cid, group, batch, monkeypatch):
     sc = [rng.randrange(r) if rng.random() < 0.8 else rng.randrange(3) for _ in range(n)]
     want = c.to_affine(msm_pippenger(c, pts, sc, FR[cid].bits))
     assert gpu_msm(ctx, cid, group, pts, sc, True) == want
+
+
+@pytest.mark.parametrize("cid,group", [(BN254, 1), (BLS12_381, 2)])
+def test_msm_batch_matches_single_calls(ctx, cid, group):
+    """zkb_msm_batch: k MSMs over slices of two resident SRS (different offsets and lengths, an empty one, Montgomery
+    scalars) give exactly what k single zkb_msm_mont calls give, and the first one what the oracle gives."""
+    c = CURVES[(cid, group)]
+    rng = random.Random(7 * cid + group)
+    n = 700 if group == 1 else 260
+    pts = H.multiples(cid, group, n, start=31)
+    xy, inf = H.points_array(cid, group, pts)
+    srs_a = ctx.srs_upload(cid, group, xy, inf)
+    srs_b = ctx.srs_upload(cid, group, xy[::-1].copy(), inf[::-1].copy(), precompute=False)
+    shapes = [(srs_a, 0, n), (srs_b, 5, 100), (srs_a, n - 3, 10), (srs_b, 0, 0), (srs_a, 17, 1), (srs_a, 0, 300),
+              (srs_b, 100, n), (srs_a, 1, 2), (srs_a, 200, 64)]
+    scalars = [H.fr_array(cid, [rng.randrange(c.r) for _ in range(cnt)], mont=True) for _, _, cnt in shapes]
+    got = ctx.msm_batch([s for s, _, _ in shapes], scalars, [o for _, o, _ in shapes], mont=True)
+    for (srs, off, cnt), sc, (gxy, ginf) in zip(shapes, scalars, got):
+        wxy, winf = ctx.msm(srs, sc, base_offset=off, mont=True) if cnt else (None, True)
+        assert ginf == winf
+        if not winf:
+            assert np.array_equal(gxy, wxy)
+    want = c.to_affine(msm_naive(c, pts, H.fr_ints(cid, scalars[0], mont=True)))
+    assert H.array_point(cid, group, *got[0]) == want
+    srs_a.free()
+    srs_b.free()
