@@ -395,6 +395,13 @@ class Context:
         self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), _addr(out), out_len))
         return out
 
+    def fr_prefix_product(self, curve, a_mont):
+        """out[i] = a[0] * ... * a[i - 1] (out[0] = 1)"""
+        a = _fr(a_mont, "elements")
+        out = _out_like(a, a.shape[0])
+        self._check(self.lib.zkb_fr_prefix_product(self.handle, curve, _addr(a), _addr(out), a.shape[0]))
+        return out
+
     def fr_batch_inverse(self, curve, a_mont):
         a = _fr(a_mont, "elements")
         out = _out_like(a, a.shape[0])

@@ -375,11 +375,95 @@ static int batch_inverse_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, ui
   return ZKB_OK;
 }
 
+// ---- exclusive prefix products: out[i] = in[0] * ... * in[i - 1], out[0] = 1 -----------------------------------
+// (the grand-product accumulator z of PLONK's permutation argument, plonk/src/ahp/indexer/permutation.rs:111-118)
+// Three phases over chunks of kScanChunk consecutive elements: chunk products, one block scans them, chunks re-walked.
+constexpr int kScanChunk = 128;
+template <class FrP>
+__global__ void k_prefix_chunk_products(const Fp<FrP>* __restrict__ in, size_t n, Fp<FrP>* __restrict__ partial) {
+  using Fr = Fp<FrP>;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * kScanChunk;
+  if (lo >= n) return;
+  size_t hi = lo + kScanChunk < n ? lo + kScanChunk : n;
+  Fr acc = ld_vec(&in[lo]);
+  for (size_t i = lo + 1; i < hi; i++) acc = Fr::mul(acc, ld_vec(&in[i]));
+  st_vec(&partial[t], acc);
+}
+// one block: partial[j] <- product of the chunk products before chunk j (exclusive)
+template <class FrP>
+__global__ void __launch_bounds__(1024) k_prefix_scan_partials(Fp<FrP>* partial, size_t m) {
+  using Fr = Fp<FrP>;
+  __shared__ Fr sh[1024];
+  const size_t per = (m + blockDim.x - 1) / blockDim.x;
+  const size_t lo = threadIdx.x * per, hi = lo + per < m ? lo + per : m;
+  Fr total = Fr::one();
+  for (size_t i = lo; i < hi; i++) total = Fr::mul(total, ld_vec_rw(&partial[i]));
+  sh[threadIdx.x] = total;
+  __syncthreads();
+  for (unsigned off = 1; off < blockDim.x; off <<= 1) {           // inclusive Hillis-Steele scan of the per-thread totals
+    Fr v = sh[threadIdx.x];
+    const bool take = threadIdx.x >= off;
+    Fr u = take ? sh[threadIdx.x - off] : Fr::one();
+    __syncthreads();
+    if (take) sh[threadIdx.x] = Fr::mul(u, v);
+    __syncthreads();
+  }
+  Fr run = threadIdx.x ? sh[threadIdx.x - 1] : Fr::one();
+  for (size_t i = lo; i < hi; i++) {
+    Fr v = ld_vec_rw(&partial[i]);
+    st_vec(&partial[i], run);
+    run = Fr::mul(run, v);
+  }
+}
+template <class FrP>
+__global__ void k_prefix_apply(const Fp<FrP>* __restrict__ in, size_t n, const Fp<FrP>* __restrict__ partial,
+                               Fp<FrP>* __restrict__ out) {
+  using Fr = Fp<FrP>;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * kScanChunk;
+  if (lo >= n) return;
+  size_t hi = lo + kScanChunk < n ? lo + kScanChunk : n;
+  Fr run = ld_vec(&partial[t]);
+  for (size_t i = lo; i < hi; i++) {
+    Fr v = ld_vec(&in[i]);
+    st_vec(&out[i], run);
+    run = Fr::mul(run, v);
+  }
+}
+template <class FrP>
+static int prefix_product_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, uint64_t* out, size_t n) {
+  using Fr = Fp<FrP>;
+  Scratch ws(ctx, st);
+  Fr *d_in, *d_out, *d_part;
+  const size_t m = (n + kScanChunk - 1) / kScanChunk;
+  ZKB_TRY(ws.alloc(&d_in, n));
+  ZKB_TRY(ws.alloc(&d_out, n));
+  ZKB_TRY(ws.alloc(&d_part, m));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyDefault, st));
+  ZKB_LAUNCH(ctx, (k_prefix_chunk_products<FrP>), ceil_div(m, 128), 128, 0, st, (const Fr*)d_in, n, d_part);
+  ZKB_LAUNCH(ctx, (k_prefix_scan_partials<FrP>), 1, 1024, 0, st, d_part, m);
+  ZKB_LAUNCH(ctx, (k_prefix_apply<FrP>), ceil_div(m, 128), 128, 0, st, (const Fr*)d_in, n, (const Fr*)d_part, d_out);
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 }  // namespace zkb
 
 using namespace zkb;
 
 extern "C" {
+
+int zkb_fr_prefix_product(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n) {
+  if (!ctx || (n && (!in_mont || !out_mont))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "prefix_product: unknown curve %d", curve);
+  if (n == 0) return ZKB_OK;
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  return curve == ZKB_BLS12_381 ? prefix_product_t<BlsFr>(ctx, ctx->main, in_mont, out_mont, n)
+                                : prefix_product_t<BnFr>(ctx, ctx->main, in_mont, out_mont, n);
+}
 
 int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t n, const uint64_t z_mont[4], uint64_t* q_mont,
                         uint64_t rem_mont[4]) {

@@ -268,6 +268,10 @@ int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* p
 /* ark_ff::batch_inversion (marlin/src/ahp/prover.rs:365-367): out[i] = 1 / in[i], zeros stay zero. */
 int zkb_fr_batch_inverse(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n);
 
+/* out[i] = in[0] * ... * in[i - 1], out[0] = 1: the grand-product accumulator z of PLONK's permutation argument
+ * (plonk/src/ahp/indexer/permutation.rs:111-118: z.push(acc); acc *= perms[i]).  Host or device buffers. */
+int zkb_fr_prefix_product(zkb_ctx* ctx, int curve, const uint64_t* in_mont, uint64_t* out_mont, size_t n);
+
 /* Elementwise Fr vector operations (the pointwise loops of marlin/src/ahp/prover.rs:246-305,357-411):
  * op 0: a + b  1: a - b  2: a * b  3: s * a  4: a + s * b  5: s - a  6: a + s   (b / s may be NULL when unused) */
 int zkb_fr_vec_op(zkb_ctx* ctx, int curve, int op, const uint64_t* a_mont, const uint64_t* b_mont, const uint64_t* s_mont,

@@ -57,3 +57,31 @@ class MockContext:
         fr = FR[curve]
         vals = H.u64_to_ints(np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4))
         return H.ints_to_u64([fr.to_mont(v) if to_mont else fr.from_mont(v) for v in vals], 4)
+
+    def fr_prefix_product(self, curve, a):
+        p = FR[curve].p
+        out, acc = [], 1
+        for x in self._ints(curve, a):
+            out.append(acc)
+            acc = acc * x % p
+        return H.fr_array(curve, out)
+
+    def poly_eval(self, curve, p_mont, z_mont):
+        p = FR[curve].p
+        z = self._ints(curve, z_mont)[0]
+        acc = 0
+        for c in reversed(self._ints(curve, p_mont)):
+            acc = (acc * z + c) % p
+        return H.fr_array(curve, [acc])[0]
+
+    def poly_lincomb(self, curve, polys, coeffs_mont, shifts=None, out_len=None):
+        p = FR[curve].p
+        cs = self._ints(curve, coeffs_mont)
+        shifts = shifts or [0] * len(polys)
+        n = out_len if out_len is not None else max([len(q) + s for q, s in zip(polys, shifts)] + [0])
+        out = [0] * n
+        for q, c, s in zip(polys, cs, shifts):
+            for i, v in enumerate(self._ints(curve, q)):
+                if i + s < n:
+                    out[i + s] = (out[i + s] + c * v) % p
+        return H.fr_array(curve, out) if n else np.zeros((0, 4), dtype=np.uint64)
