@@ -652,7 +652,15 @@ struct MsmEngine {
       return ZKB_OK;
     }
     MsmGeom g;
-    g.c = srs->c; g.W = srs->W; g.B = 1u << (g.c - 1); g.precomp = srs->precomp;
+    g.c = srs->c; g.W = srs->W; g.precomp = srs->precomp;
+    if (!g.precomp) {
+      // without window tables nothing ties the window width to the SRS: choose it for THIS call's n, so that a short
+      // MSM over a slice of a long key (a Marlin commitment to a low-degree polynomial, a Pedersen row commitment) does
+      // not pay the bucket reduction of the full-length one
+      g.c = msm_pick_c(n, 0, FrP::BITS);
+      g.W = msm_windows(FrP::BITS, g.c);
+    }
+    g.B = 1u << (g.c - 1);
     g.n_srs = (uint32_t)srs->n; g.n_sets = g.precomp ? 1u : (uint32_t)g.W;
     if (g.precomp && n * (size_t)g.W <= kSmallMsmTerms) {
       Scratch ws(ctx, st);

@@ -60,11 +60,11 @@ __global__ void k_powers(Fp<FrP>* out, size_t count, const Fp<FrP>* base_p, cons
 // One DIT pass: stages s0 .. s0+k-1 on tiles of 2^(k+t) elements.
 //   element e of a tile: lo = e & (2^t - 1), mid = e >> t
 //   global index        = (hi << (s0 + k)) | (mid << s0) | (lo_base + lo)
-template <class FrP>
-__global__ void __launch_bounds__(512)
+template <class FrP, int MIN_BLOCKS>
+__global__ void __launch_bounds__(256, MIN_BLOCKS)
 k_ntt_pass(const Fp<FrP>* src, Fp<FrP>* dst, const Fp<FrP>* __restrict__ tw, unsigned log_n, unsigned s0, unsigned k,
            unsigned t, int first, const Fp<FrP>* __restrict__ pre_scale, const Fp<FrP>* __restrict__ post_scale,
-           const Fp<FrP>* __restrict__ post_const) {
+           const Fp<FrP>* __restrict__ post_const, int radix4) {
   using Fr = Fp<FrP>;
   extern __shared__ uint32_t sm[];
   const unsigned E = 1u << (k + t);
@@ -85,7 +85,37 @@ k_ntt_pass(const Fp<FrP>* src, Fp<FrP>* dst, const Fp<FrP>* __restrict__ tw, uns
   }
   __syncthreads();
 
-  for (unsigned q = 0; q < k; q++) {
+  // Two stages per shared-memory round trip (radix-4 step: four elements in registers, three twiddles, four
+  // multiplications, one barrier) while at least two stages remain; an odd stage count ends with one radix-2 stage.
+  unsigned q = 0;
+  if (radix4) {
+    for (; q + 1 < k; q += 2) {
+      for (unsigned i = threadIdx.x; i < E / 4; i += blockDim.x) {
+        const unsigned lo = i & lo_mask, m = i >> t;
+        const unsigned mid0 = ((m >> q) << (q + 2)) | (m & ((1u << q) - 1));
+        const unsigned h = 1u << (q + t);
+        const unsigned e0 = (mid0 << t) | lo, e1 = e0 + h, e2 = e0 + 2 * h, e3 = e0 + 3 * h;
+        const size_t j = ((size_t)(mid0 & ((1u << q) - 1)) << s0) | (lo_base + lo);
+        const unsigned sh = log_n - 1 - (s0 + q);
+        const Fr w1 = ld_vec(&tw[j << sh]);                                       // stage q, both pairs
+        const Fr w2a = ld_vec(&tw[j << (sh - 1)]);                                // stage q + 1, pair (e0, e2)
+        const Fr w2b = ld_vec(&tw[(j + (size_t(1) << (q + s0))) << (sh - 1)]);    // stage q + 1, pair (e1, e3)
+        Fr a0, a1, a2, a3;
+#pragma unroll
+        for (int x = 0; x < Fr::N; x++) { a0.v[x] = sm[x * E + e0]; a1.v[x] = sm[x * E + e1]; a2.v[x] = sm[x * E + e2]; a3.v[x] = sm[x * E + e3]; }
+        a1 = Fr::mul(a1, w1);
+        a3 = Fr::mul(a3, w1);
+        Fr b0 = Fr::add(a0, a1), b1 = Fr::sub(a0, a1), b2 = Fr::add(a2, a3), b3 = Fr::sub(a2, a3);
+        b2 = Fr::mul(b2, w2a);
+        b3 = Fr::mul(b3, w2b);
+        a0 = Fr::add(b0, b2); a2 = Fr::sub(b0, b2); a1 = Fr::add(b1, b3); a3 = Fr::sub(b1, b3);
+#pragma unroll
+        for (int x = 0; x < Fr::N; x++) { sm[x * E + e0] = a0.v[x]; sm[x * E + e1] = a1.v[x]; sm[x * E + e2] = a2.v[x]; sm[x * E + e3] = a3.v[x]; }
+      }
+      __syncthreads();
+    }
+  }
+  for (; q < k; q++) {
     for (unsigned i = threadIdx.x; i < E / 2; i += blockDim.x) {
       unsigned lo = i & lo_mask, m = i >> t;
       unsigned mid0 = ((m >> q) << (q + 1)) | (m & ((1u << q) - 1));
@@ -193,16 +223,26 @@ static int ntt_run_t(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data
     unsigned E = 1u << (k + t);
     const Fr* src = p == 0 ? data : scratch;
     Fr* dst = (p == np - 1 && np > 1) ? data : scratch;
+    static const int radix4 = []() { const char* e = getenv("ZKB_NTT_RADIX4"); return e ? atoi(e) : 1; }();
     static const unsigned div = []() { const char* e = getenv("ZKB_NTT_DIV"); unsigned v = e ? (unsigned)atoi(e) : 4u; return v < 2 ? 2u : v; }();
     unsigned threads = E / div < 32 ? 32 : E / div;      // div / 2 butterflies per thread and stage; measured at 2^21: 0.578 / 0.520 / 0.538 ms for div = 2 / 4 / 8
     size_t tiles = dom->n >> (k + t);
-    if (threads > 512) threads = 512;                    // __launch_bounds__ of the pass kernel; the loops stride by blockDim
+    if (threads > 256) threads = 256;                    // __launch_bounds__ of the pass kernel; the loops stride by blockDim
     const size_t smem = sizeof(uint32_t) * Fr::N * E;
-    if (smem > 48 * 1024)                                // opt-in above 48 KiB is a per-device function attribute: set per call
-      ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)k_ntt_pass<FrP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ZKB_LAUNCH(ctx, (k_ntt_pass<FrP>), (unsigned)tiles, threads, smem, st, src, dst, tw, log_n, s0, k,
-               t, p == 0 ? 1 : 0, p == 0 ? pre : (const Fr*)nullptr, p == np - 1 ? post : (const Fr*)nullptr,
-               p == np - 1 ? pconst : (const Fr*)nullptr);
+    // resident blocks per SM the kernel is compiled for: the radix-4 step wants ~100 registers (2 blocks of 256 threads),
+    // capped at 80 / 64 it spills 4 / 40 bytes and 3 / 4 blocks fit
+    static const int occ = []() { const char* e = getenv("ZKB_NTT_OCC"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : v > 4 ? 4 : v; }();
+    auto launch = [&](auto kernel) -> int {
+      if (smem > 48 * 1024)                              // opt-in above 48 KiB is a per-device function attribute: set per call
+        ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ZKB_LAUNCH(ctx, kernel, (unsigned)tiles, threads, smem, st, src, dst, tw, log_n, s0, k, t, p == 0 ? 1 : 0,
+                 p == 0 ? pre : (const Fr*)nullptr, p == np - 1 ? post : (const Fr*)nullptr,
+                 p == np - 1 ? pconst : (const Fr*)nullptr, radix4);
+      return ZKB_OK;
+    };
+    if (occ == 2) ZKB_TRY(launch(k_ntt_pass<FrP, 2>));
+    else if (occ == 3) ZKB_TRY(launch(k_ntt_pass<FrP, 3>));
+    else ZKB_TRY(launch(k_ntt_pass<FrP, 4>));
     s0 += k;
   }
   if (np == 1) ZKB_CUDA(ctx, cudaMemcpyAsync(data, scratch, sizeof(Fr) * dom->n, cudaMemcpyDeviceToDevice, st));

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 from . import kzg10 as _kzg
-from .backend import Context
+from .backend import Context, is_dev
 from .fs_rng import ChaChaRng, affine_to_bytes, fr_to_bytes
 from .groth16 import FR_MODULUS
 from .r1cs import ints_to_limbs, limbs_to_int
@@ -134,9 +134,9 @@ def _group_gen(curve, log_n):
 
 
 def _strip(poly):
-    """DensePolynomial::from_coefficients_vec: trailing zero coefficients dropped"""
-    nz = np.flatnonzero(poly.any(axis=1))
-    return np.ascontiguousarray(poly[:nz[-1] + 1]) if len(nz) else poly[:0]
+    """DensePolynomial::from_coefficients_vec: trailing zero coefficients dropped (host array or resident tensor)"""
+    from .marlin import contig, trim
+    return contig(trim(poly))
 
 
 class Index:
@@ -147,45 +147,54 @@ class Index:
 
 
 def _interpolate(ctx, curve, evals_n, log_n):
-    a = np.array(evals_n, dtype=np.uint64, copy=True)
+    from .marlin import pad
+    a = pad(evals_n, 1 << log_n)                                        # always a copy: the transform works in place
     ctx.ntt(curve, a, log_n, inverse=True)
     return a
 
 
 def _coset_fft_4n(ctx, curve, poly, log_4n):
-    a = np.zeros((1 << log_4n, 4), dtype=np.uint64)
-    a[:len(poly)] = poly
+    from .marlin import pad
+    a = pad(poly, 1 << log_4n)
     ctx.ntt(curve, a, log_4n, coset=True)
     return a
 
 
-def index(ctx, curve, cs, ks):
-    """AHPForPLONK::index (ahp/indexer/mod.rs:166-259)"""
+def index(ctx, curve, cs, ks, resident=False):
+    """AHPForPLONK::index (ahp/indexer/mod.rs:166-259).  resident=True keeps every vector of the index and of the
+    prover's round state in HBM (CUDA tensors, like marlin.Ops): the primitives then exchange device pointers."""
+    from .marlin import Ops
     p = FR_MODULUS[curve]
+    ops = Ops(ctx, curve, resident)
     log_n = _log2_domain(curve, cs.n)
     n = 1 << log_n
     log_4n = _log2_domain(curve, 4 * n)
     idx = Index()
+    idx.resident = resident
     idx.curve, idx.n, idx.log_n, idx.log_4n, idx.ks = curve, n, log_n, log_4n, [int(k) % p for k in ks]
     idx.group_gen = _group_gen(curve, log_n)
     # Composer::compose (synthesize.rs:69-108): selectors padded with zeros, sigma = k_c * w^i at the permuted wire
-    roots = ctx.fr_powers(curve, _mont(ctx, curve, idx.group_gen), n)
+    roots = ctx.fr_powers(curve, _mont(ctx, curve, idx.group_gen), n, device=ops.device)
     idx.roots = roots
-    scaled = np.stack([ctx.fr_vec_op(curve, Context.VEC_SCALE, roots, s=_mont(ctx, curve, k)) for k in idx.ks])
+    scaled = ops.cat([ctx.fr_vec_op(curve, Context.VEC_SCALE, roots, s=_mont(ctx, curve, k)) for k in idx.ks])   # [4 n, 4]
     cols, rows = cs.wire_permutation(n)
-    sel = {k: _mont_vec(ctx, curve, v, n) for k, v in cs.q.items()}
+    sel = {k: ops.put(_mont_vec(ctx, curve, v, n)) for k, v in cs.q.items()}
     for c in range(4):
-        sel["sigma_%d" % c] = np.ascontiguousarray(scaled[cols[c], rows[c]])
+        sel["sigma_%d" % c] = ops.take(scaled, cols[c] * n + rows[c])
     for label in SELECTOR_LABELS:
         poly = _interpolate(ctx, curve, sel[label], log_n)
         idx.polys[label], idx.evals_n[label] = _strip(poly), sel[label]
         idx.evals_4n[label] = _coset_fft_4n(ctx, curve, idx.polys[label], log_4n)
     v_poly = np.zeros((n + 1, 4), dtype=np.uint64)                      # x^n - 1 (utils.rs:28-34)
     v_poly[0], v_poly[n] = _mont(ctx, curve, p - 1), _mont(ctx, curve, 1)
-    idx.v_4n_inversed = ctx.fr_batch_inverse(curve, _coset_fft_4n(ctx, curve, v_poly, log_4n))
+    idx.v_4n_inversed = ctx.fr_batch_inverse(curve, _coset_fft_4n(ctx, curve, ops.put(v_poly), log_4n))
     unit = np.zeros((n, 4), dtype=np.uint64)
     unit[0] = _mont(ctx, curve, 1)
-    idx.l1_4n = _coset_fft_4n(ctx, curve, _strip(_interpolate(ctx, curve, unit, log_n)), log_4n)   # utils.rs:41-45
+    idx.l1_4n = _coset_fft_4n(ctx, curve, _strip(_interpolate(ctx, curve, ops.put(unit), log_n)), log_4n)   # utils.rs:41-45
+    lin = np.zeros((2, 4), dtype=np.uint64)
+    lin[1] = _mont(ctx, curve, 1)
+    idx.linear_4n = _coset_fft_4n(ctx, curve, ops.put(lin), log_4n)     # coset_fft(&[0, 1]) of permutation.rs:139-142
+    ops.release()                                                       # torch's current stream goes back to the caller
     return idx
 
 
@@ -195,9 +204,11 @@ class ProverState:
 
 def prover_init(ctx, cs, idx):
     """ahp/prover.rs:69-93"""
+    from .marlin import Ops
     ps = ProverState()
     ps.ctx, ps.index = ctx, idx
-    pi_poly = _strip(_interpolate(ctx, idx.curve, _mont_vec(ctx, idx.curve, cs.public_inputs(), idx.n), idx.log_n))
+    ps.ops = Ops(ctx, idx.curve, idx.resident)      # resident: released by prove(); round-level callers call ps.ops.release()
+    pi_poly = _strip(_interpolate(ctx, idx.curve, ps.ops.put(_mont_vec(ctx, idx.curve, cs.public_inputs(), idx.n)), idx.log_n))
     ps.pi_4n = _coset_fft_4n(ctx, idx.curve, pi_poly, idx.log_4n)
     return ps
 
@@ -207,7 +218,7 @@ def prover_first_round(ps, cs):
     ctx, idx = ps.ctx, ps.index
     ps.w_n, ps.w_4n, oracles = [], [], {}
     for k in range(4):                                                  # Composer::synthesize (synthesize.rs:114-132)
-        w = _mont_vec(ctx, idx.curve, [cs.assignment[v] for v in cs.w[k]], idx.n)
+        w = ps.ops.put(_mont_vec(ctx, idx.curve, [cs.assignment[v] for v in cs.w[k]], idx.n))
         poly = _strip(_interpolate(ctx, idx.curve, w, idx.log_n))
         oracles["w_%d" % k] = poly
         ps.w_n.append(w)
@@ -234,7 +245,8 @@ def prover_second_round(ps, beta, gamma):
     den = _factor_product(ctx, curve, ps.w_n, [idx.evals_n["sigma_%d" % k] for k in range(4)], [_mont(ctx, curve, beta)] * 4, gm)
     perms = ctx.fr_vec_op(curve, Context.VEC_MUL, num, ctx.fr_batch_inverse(curve, den))
     z = ctx.fr_prefix_product(curve, perms)                             # z[0] = 1, z[i + 1] = z[i] * perms[i]
-    closing = ctx.fr_vec_op(curve, Context.VEC_MUL, np.ascontiguousarray(z[-1:]), np.ascontiguousarray(perms[-1:]))
+    from .marlin import contig, to_host
+    closing = to_host(ctx.fr_vec_op(curve, Context.VEC_MUL, contig(z[-1:]), contig(perms[-1:])))
     if not np.array_equal(closing[0], _mont(ctx, curve, 1)):
         raise AssertionError("z[n - 1] * perms[n - 1] != 1: the copy constraints are not satisfied")   # permutation.rs:118
     z_poly = _strip(_interpolate(ctx, curve, z, idx.log_n))
@@ -259,12 +271,11 @@ def prover_third_round(ps, alpha):
     # permutation part
     beta, gamma = ps.beta, ps.gamma
     gm = _mont(ctx, curve, gamma)
-    lin = np.zeros((2, 4), dtype=np.uint64)
-    lin[1] = _mont(ctx, curve, 1)
-    linear_4n = _coset_fft_4n(ctx, curve, lin, idx.log_4n)              # coset_fft(&[0, 1])
+    linear_4n = idx.linear_4n
     num = _factor_product(ctx, curve, w, [linear_4n] * 4, [_mont(ctx, curve, k * beta % p) for k in idx.ks], gm)
     den = _factor_product(ctx, curve, w, [e4["sigma_%d" % k] for k in range(4)], [_mont(ctx, curve, beta)] * 4, gm)
-    z_next = np.ascontiguousarray(np.roll(ps.z_4n, -4, axis=0))         # next = i + 4, wrapping to i % 4 in the last block
+    # next = i + 4, wrapping to i % 4 in the last block: a rotation by four
+    z_next = ps.z_4n.roll(-4, 0).contiguous() if is_dev(ps.z_4n) else np.ascontiguousarray(np.roll(ps.z_4n, -4, axis=0))
     diff = op(V.VEC_SUB, op(V.VEC_MUL, num, ps.z_4n), op(V.VEC_MUL, den, z_next))
     start = op(V.VEC_MUL, op(V.VEC_ADDC, ps.z_4n, s=_mont(ctx, curve, p - 1)), idx.l1_4n)     # (z - 1) * l1
     t_perm = op(V.VEC_AXPY, op(V.VEC_SCALE, diff, s=_mont(ctx, curve, alpha)), start, s=_mont(ctx, curve, alpha * alpha % p))
@@ -319,7 +330,7 @@ def lc_polynomial(ctx, curve, lc, polys):
     """the polynomial of a linear combination (EvaluationsProvider for Vec<LabeledPolynomial>, ahp/evaluations.rs:24-48)"""
     terms = [(c, polys[label]) for c, label in lc if len(polys[label])]
     if not terms:
-        return np.zeros((0, 4), dtype=np.uint64)
+        return polys[lc[0][1]][:0]
     coeffs = ctx.fr_convert(curve, ints_to_limbs([c for c, _ in terms]), to_mont=True)
     return ctx.poly_lincomb(curve, [q for _, q in terms], coeffs)
 
@@ -336,8 +347,13 @@ def verifier_equality_check(ctx, idx, beta, gamma, alpha, zeta, evals, public_in
     """ahp/verifier.rs:105-150 (the verifier's side, here so that a proof can be self-checked on the same primitives)"""
     curve, p, n = idx.curve, FR_MODULUS[idx.curve], idx.n
     v_zeta = (pow(zeta, n, p) - 1) % p
-    pi_poly = _strip(_interpolate(ctx, curve, _mont_vec(ctx, curve, list(public_inputs), n), idx.log_n))
-    pi_zeta = _eval(ctx, curve, pi_poly, zeta)
+    from .marlin import Ops
+    ops = Ops(ctx, curve, idx.resident)
+    try:
+        pi_poly = _strip(_interpolate(ctx, curve, ops.put(_mont_vec(ctx, curve, list(public_inputs), n)), idx.log_n))
+        pi_zeta = _eval(ctx, curve, pi_poly, zeta)
+    finally:
+        ops.release()
     l1 = first_lagrange_at(idx, zeta)
     prod = evals["z"]
     for k in range(3):
@@ -394,7 +410,7 @@ def _pc_commit(ck, labeled):
             from .backend import point_words
             comms.append(((np.zeros(point_words(curve, _lib.G1), dtype=np.uint64), True), None))
         else:
-            comms.append((ck.msm_g(np.ascontiguousarray(P.coeffs[:1]), 0), None))
+            comms.append((ck.msm_g(P.coeffs[:1], 0), None))
     return comms, [(_kzg.Randomness(), None)] * len(labeled)
 
 
@@ -408,11 +424,11 @@ class ProverKey:
     pass
 
 
-def keygen(ctx, srs, cs, ks):
+def keygen(ctx, srs, cs, ks, resident=False):
     """Plonk::keygen (lib.rs:62-91): index, PC::trim(srs, index.size()), commitments to the 11 index polynomials.
     srs: marlin.UniversalParams (marlin.universal_setup) -> (ProverKey, verifier-key dict)"""
     from . import marlin as _marlin
-    idx = index(ctx, srs.curve, cs, ks)
+    idx = index(ctx, srs.curve, cs, ks, resident=resident)
     if srs.max_degree() < idx.n:
         raise CircuitTooLarge()
     ck, rk = _marlin.pc_trim(ctx, srs, idx.n)
@@ -439,42 +455,45 @@ def prove(ctx, pk, cs, fs_rng=None):
     if fs_rng is None:
         fs_rng = FiatShamirRng(b"PLONK" + b"".join(fr_to_bytes(x) for x in cs.public_inputs()), curve)
     ps = prover_init(ctx, cs, idx)
-    polys = dict(idx.polys)
+    try:
+        polys = dict(idx.polys)
 
-    first = prover_first_round(ps, cs)
-    first_comms, first_rands = _pc_commit(ck, _labeled(first, ORACLE_LABELS[:4]))
-    fs_rng.absorb(_comms_to_bytes(curve, first_comms))
-    beta, gamma = fs_rng.rand_fr(), fs_rng.rand_fr()                    # verifier_first_round
-    polys.update(first)
+        first = prover_first_round(ps, cs)
+        first_comms, first_rands = _pc_commit(ck, _labeled(first, ORACLE_LABELS[:4]))
+        fs_rng.absorb(_comms_to_bytes(curve, first_comms))
+        beta, gamma = fs_rng.rand_fr(), fs_rng.rand_fr()                    # verifier_first_round
+        polys.update(first)
 
-    second = prover_second_round(ps, beta, gamma)
-    second_comms, second_rands = _pc_commit(ck, _labeled(second, ["z"]))
-    fs_rng.absorb(_comms_to_bytes(curve, second_comms))
-    alpha = fs_rng.rand_fr()                                            # verifier_second_round
-    polys.update(second)
+        second = prover_second_round(ps, beta, gamma)
+        second_comms, second_rands = _pc_commit(ck, _labeled(second, ["z"]))
+        fs_rng.absorb(_comms_to_bytes(curve, second_comms))
+        alpha = fs_rng.rand_fr()                                            # verifier_second_round
+        polys.update(second)
 
-    third = prover_third_round(ps, alpha)
-    third_comms, third_rands = _pc_commit(ck, _labeled(third, ORACLE_LABELS[5:]))
-    fs_rng.absorb(_comms_to_bytes(curve, third_comms))
-    zeta = fs_rng.rand_fr()                                             # verifier_third_round
-    polys.update(third)
+        third = prover_third_round(ps, alpha)
+        third_comms, third_rands = _pc_commit(ck, _labeled(third, ORACLE_LABELS[5:]))
+        fs_rng.absorb(_comms_to_bytes(curve, third_comms))
+        zeta = fs_rng.rand_fr()                                             # verifier_third_round
+        polys.update(third)
 
-    qs = verifier_query_set(idx, zeta)
-    lcs = construct_linear_combinations(ctx, idx, beta, gamma, alpha, zeta, polys)
-    lc_polys = {label: lc_polynomial(ctx, curve, lcs[label], polys) for label in qs}
-    evals = {label: _eval(ctx, curve, lc_polys[label], point) for label, (_, point) in qs.items()}
-    evaluations = [evals[label] for label in sorted(evals)]             # evals.sort_by label (lib.rs:171-173)
-    fs_rng.absorb(b"".join(fr_to_bytes(e) for e in evaluations))
-    epsilon = fs_rng.rand_fr()
+        qs = verifier_query_set(idx, zeta)
+        lcs = construct_linear_combinations(ctx, idx, beta, gamma, alpha, zeta, polys)
+        lc_polys = {label: lc_polynomial(ctx, curve, lcs[label], polys) for label in qs}
+        evals = {label: _eval(ctx, curve, lc_polys[label], point) for label, (_, point) in qs.items()}
+        evaluations = [evals[label] for label in sorted(evals)]             # evals.sort_by label (lib.rs:171-173)
+        fs_rng.absorb(b"".join(fr_to_bytes(e) for e in evaluations))
+        epsilon = fs_rng.rand_fr()
 
-    # one opening per query point over the linear-combination polynomials, combined with powers of epsilon
-    # (the role of PC::open_combinations, lib.rs:186-197)
-    openings = {}
-    for point_label in ("shifted_zeta", "zeta"):
-        group = [label for label in sorted(qs) if qs[label][0] == point_label]
-        point = qs[group[0]][1]
-        labeled = [_kzg.LabeledPolynomial(label, lc_polys[label]) for label in group]
-        rands = [(_kzg.Randomness(), None)] * len(group)
-        openings[point_label] = _kzg.pc_open(ck, labeled, _mont(ctx, curve, point), epsilon, rands)
+        # one opening per query point over the linear-combination polynomials, combined with powers of epsilon
+        # (the role of PC::open_combinations, lib.rs:186-197)
+        openings = {}
+        for point_label in ("shifted_zeta", "zeta"):
+            group = [label for label in sorted(qs) if qs[label][0] == point_label]
+            point = qs[group[0]][1]
+            labeled = [_kzg.LabeledPolynomial(label, lc_polys[label]) for label in group]
+            rands = [(_kzg.Randomness(), None)] * len(group)
+            openings[point_label] = _kzg.pc_open(ck, labeled, _mont(ctx, curve, point), epsilon, rands)
+    finally:
+        ps.ops.release()
     proof = Proof([first_comms, second_comms, third_comms], evaluations, openings)
     return proof, {"beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "epsilon": epsilon, "evals": evals}

@@ -103,8 +103,9 @@ def test_unsatisfied_copy_constraint_trips_the_closing_assertion(ctx):
         zp.prover_second_round(ps, 5, 6)
 
 
+@pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("cid", [BLS12_381, BN254])
-def test_keygen_prove_self_verifies(ctx, cid):
+def test_keygen_prove_self_verifies(ctx, cid, resident):
     """Plonk::{setup, keygen, prove} (plonk/src/lib.rs:53-204, test_plonk :361-376) with the Fiat-Shamir generator in the
     loop: commitments equal kg * p(beta) * G for the known trapdoor, the evaluations pass the equality check under the
     challenges the transcript produced, and each opening satisfies the KZG equation W * (beta - z) == P(beta) - v in the
@@ -116,7 +117,7 @@ def test_keygen_prove_self_verifies(ctx, cid):
     setup_rng = random.Random(5)
     beta_t, kg = setup_rng.randrange(1, p), setup_rng.randrange(1, p)          # the first two draws of universal_setup
     srs = zm.universal_setup(ctx, cid, 64, random.Random(5))
-    pk, vk = zp.keygen(ctx, srs, cs, KS)
+    pk, vk = zp.keygen(ctx, srs, cs, KS, resident=resident)
     proof, ch = zp.prove(ctx, pk, cs)
     idx = pk.index
     c1 = CURVES[(cid, 1)]
