@@ -230,8 +230,10 @@ static int ntt_run_t(zkb_ctx* ctx, cudaStream_t st, NttDomain* dom, void* d_data
     if (threads > 256) threads = 256;                    // __launch_bounds__ of the pass kernel; the loops stride by blockDim
     const size_t smem = sizeof(uint32_t) * Fr::N * E;
     // resident blocks per SM the kernel is compiled for: the radix-4 step wants ~100 registers (2 blocks of 256 threads),
-    // capped at 80 / 64 it spills 4 / 40 bytes and 3 / 4 blocks fit
-    static const int occ = []() { const char* e = getenv("ZKB_NTT_OCC"); int v = e ? atoi(e) : 3; return v < 2 ? 2 : v > 4 ? 4 : v; }();
+    // capped at 80 / 64 it spills 4 / 40 bytes and 3 / 4 blocks fit.  Measured (fft, 2^21 / 2^24 BLS12-381, ms;
+    // profiles/r2q_ntt_radix4_occ.txt): radix-2 only 0.614 / 5.26, 0.551 / 4.58, 0.527 / 4.30 for 2 / 3 / 4 blocks;
+    // with radix-4 steps 0.528 / 4.60, 0.505 / 4.21, 0.502 / 4.11 -> default radix-4, 4 blocks
+    static const int occ = []() { const char* e = getenv("ZKB_NTT_OCC"); int v = e ? atoi(e) : 4; return v < 2 ? 2 : v > 4 ? 4 : v; }();
     auto launch = [&](auto kernel) -> int {
       if (smem > 48 * 1024)                              // opt-in above 48 KiB is a per-device function attribute: set per call
         ZKB_CUDA(ctx, cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -212,71 +212,103 @@ k_spmv_long(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ c
   }
 }
 
+// ---- host-or-device buffers ------------------------------------------------------------------------------------
+// A caller that keeps its vectors resident in HBM (the Marlin / PLONK host layers) passes device pointers: those are
+// used IN PLACE (no staging copy) and a call whose outputs all live on the device returns without synchronising -- the
+// work is ordered on the library's stream, which the resident host layers share (marlin.Ops).  Host buffers are staged
+// through stream-ordered scratch as before and the call returns when the result has landed.
+static bool on_device(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice;
+}
+// device view of `count` elements at `src`: the pointer itself, or a staged copy
+template <class T>
+static int stage_in(zkb_ctx* ctx, Scratch& ws, cudaStream_t st, const void* src, size_t count, const T** out) {
+  if (count == 0 || on_device(src)) { *out = (const T*)src; return ZKB_OK; }
+  T* d;
+  ZKB_TRY(ws.alloc(&d, count));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyDefault, st));
+  *out = d;
+  return ZKB_OK;
+}
+// device buffer a kernel writes `count` elements to: `dst` itself when it is device memory, else scratch (*staged = true)
+template <class T>
+static int stage_out(zkb_ctx* ctx, Scratch& ws, void* dst, size_t count, T** out, bool* staged) {
+  (void)ctx;
+  if (on_device(dst)) { *out = (T*)dst; *staged = false; return ZKB_OK; }
+  *staged = true;
+  return ws.alloc(out, count ? count : 1);
+}
+// copy a staged result back and wait; a device-resident result needs neither
+template <class T>
+static int finish_out(zkb_ctx* ctx, cudaStream_t st, void* dst, const T* d, size_t count, bool staged) {
+  if (!staged) return ZKB_OK;
+  if (count) ZKB_CUDA(ctx, cudaMemcpyAsync(dst, d, count * sizeof(T), cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 template <class FrP>
 static int vec_op_t(zkb_ctx* ctx, cudaStream_t st, int op, const uint64_t* a, const uint64_t* b, const uint64_t* s_host,
                     uint64_t* out, size_t n) {
   using Fr = Fp<FrP>;
   Scratch ws(ctx, st);
-  Fr *d_a, *d_b, *d_o;
   const bool binary = op == 0 || op == 1 || op == 2 || op == 4;
-  ZKB_TRY(ws.alloc(&d_a, n));
-  ZKB_TRY(ws.alloc(&d_b, binary ? n : 1));
-  ZKB_TRY(ws.alloc(&d_o, n));
+  const Fr *d_a, *d_b = nullptr;
+  Fr* d_o;
+  bool staged;
+  ZKB_TRY(stage_in(ctx, ws, st, a, n, &d_a));
+  if (binary) ZKB_TRY(stage_in(ctx, ws, st, b, n, &d_b));
+  ZKB_TRY(stage_out(ctx, ws, out, n, &d_o, &staged));
   Fr s = Fr::zero();
   if (s_host) memcpy(s.v, s_host, 32);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_a, a, n * sizeof(Fr), cudaMemcpyDefault, st));
-  if (binary) ZKB_CUDA(ctx, cudaMemcpyAsync(d_b, b, n * sizeof(Fr), cudaMemcpyDefault, st));
   unsigned blocks = ceil_div(n, 256);
   if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-  ZKB_LAUNCH(ctx, (k_fr_vec_op<FrP>), blocks, 256, 0, st, op, (const Fr*)d_a, (const Fr*)d_b, s, d_o, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+  ZKB_LAUNCH(ctx, (k_fr_vec_op<FrP>), blocks, 256, 0, st, op, d_a, d_b, s, d_o, n);
+  return finish_out(ctx, st, out, d_o, n, staged);
 }
 template <class FrP>
 static int powers_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* base, const uint64_t* scale, uint64_t* out, size_t n) {
   using Fr = Fp<FrP>;
   Scratch ws(ctx, st);
   Fr* d_o;
-  ZKB_TRY(ws.alloc(&d_o, n));
+  bool staged;
+  ZKB_TRY(stage_out(ctx, ws, out, n, &d_o, &staged));
   Fr b, sc = Fr::one();
   memcpy(b.v, base, 32);
   if (scale) memcpy(sc.v, scale, 32);
   ZKB_LAUNCH(ctx, (k_fr_powers<FrP>), ceil_div(ceil_div(n, 32), 128), 128, 0, st, b, sc, d_o, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_o, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+  return finish_out(ctx, st, out, d_o, n, staged);
 }
 template <class FrP>
 static int spmv_t(zkb_ctx* ctx, cudaStream_t st, const zkb_csr* m, const uint64_t* x, size_t n_cols, uint64_t* y) {
   using Fr = Fp<FrP>;
   Scratch ws(ctx, st);
-  uint32_t *d_ptr, *d_col;
-  Fr *d_coeff, *d_x, *d_y;
-  ZKB_TRY(ws.alloc(&d_ptr, m->n_rows + 1));
-  ZKB_TRY(ws.alloc(&d_col, m->nnz));
-  ZKB_TRY(ws.alloc(&d_coeff, m->nnz));
-  ZKB_TRY(ws.alloc(&d_x, n_cols));
-  ZKB_TRY(ws.alloc(&d_y, m->n_rows));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_ptr, m->row_ptr, (m->n_rows + 1) * 4, cudaMemcpyDefault, st));
-  if (m->nnz) {
-    ZKB_CUDA(ctx, cudaMemcpyAsync(d_col, m->col_idx, m->nnz * 4, cudaMemcpyDefault, st));
-    ZKB_CUDA(ctx, cudaMemcpyAsync(d_coeff, m->coeff_mont, m->nnz * sizeof(Fr), cudaMemcpyDefault, st));
-  }
-  if (n_cols) ZKB_CUDA(ctx, cudaMemcpyAsync(d_x, x, n_cols * sizeof(Fr), cudaMemcpyDefault, st));
+  const uint32_t *d_ptr, *d_col;
+  const Fr *d_coeff, *d_x;
+  Fr* d_y;
+  bool staged;
+  ZKB_TRY(stage_in(ctx, ws, st, m->row_ptr, m->n_rows + 1, &d_ptr));
+  ZKB_TRY(stage_in(ctx, ws, st, m->col_idx, m->nnz, &d_col));
+  ZKB_TRY(stage_in(ctx, ws, st, m->coeff_mont, m->nnz, &d_coeff));
+  ZKB_TRY(stage_in(ctx, ws, st, x, n_cols, &d_x));
+  ZKB_TRY(stage_out(ctx, ws, y, m->n_rows, &d_y, &staged));
   const size_t max_long = m->nnz / kSpmvLong + 1;
   uint32_t *d_long, *d_n_long;
   ZKB_TRY(ws.alloc(&d_long, max_long));
   ZKB_TRY(ws.alloc(&d_n_long, 1));
   ZKB_CUDA(ctx, cudaMemsetAsync(d_n_long, 0, 4, st));
-  ZKB_LAUNCH(ctx, (k_spmv_generic<FrP>), ceil_div(m->n_rows, 256), 256, 0, st, (const uint32_t*)d_ptr, (const uint32_t*)d_col,
-             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (uint32_t)m->n_rows, d_long, d_n_long);
+  ZKB_LAUNCH(ctx, (k_spmv_generic<FrP>), ceil_div(m->n_rows, 256), 256, 0, st, d_ptr, d_col, d_coeff, d_x, d_y,
+             (uint32_t)m->n_rows, d_long, d_n_long);
   unsigned long_blocks = max_long < (size_t)ctx->sm_count * 4 ? (unsigned)max_long : (unsigned)ctx->sm_count * 4;
-  ZKB_LAUNCH(ctx, (k_spmv_long<FrP>), long_blocks, 256, 0, st, (const uint32_t*)d_ptr, (const uint32_t*)d_col,
-             (const Fr*)d_coeff, (const Fr*)d_x, d_y, (const uint32_t*)d_long, (const uint32_t*)d_n_long);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(y, d_y, m->n_rows * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+  ZKB_LAUNCH(ctx, (k_spmv_long<FrP>), long_blocks, 256, 0, st, d_ptr, d_col, d_coeff, d_x, d_y, (const uint32_t*)d_long,
+             (const uint32_t*)d_n_long);
+  return finish_out(ctx, st, y, d_y, m->n_rows, staged);
 }
 
 template <class FrP>
@@ -339,9 +371,8 @@ static int lincomb_t(zkb_ctx* ctx, cudaStream_t st, size_t k, const uint64_t* co
   memset(&h, 0, sizeof h);
   h.k = (int)k;
   for (size_t j = 0; j < k; j++) {
-    Fr* d;
-    ZKB_TRY(ws.alloc(&d, lens[j]));
-    if (lens[j]) ZKB_CUDA(ctx, cudaMemcpyAsync(d, polys[j], lens[j] * sizeof(Fr), cudaMemcpyDefault, st));
+    const Fr* d;
+    ZKB_TRY(stage_in(ctx, ws, st, polys[j], lens[j], &d));
     h.poly[j] = d;
     h.len[j] = lens[j];
     h.shift[j] = shifts ? shifts[j] : 0;
@@ -349,30 +380,35 @@ static int lincomb_t(zkb_ctx* ctx, cudaStream_t st, size_t k, const uint64_t* co
   }
   LincombArgs<FrP>* d_args;
   Fr* d_out;
+  bool staged;
   ZKB_TRY(ws.alloc(&d_args, 1));
-  ZKB_TRY(ws.alloc(&d_out, out_len));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_args, &h, sizeof h, cudaMemcpyDefault, st));
+  ZKB_TRY(stage_out(ctx, ws, out, out_len, &d_out, &staged));
+  ZKB_CUDA(ctx, cudaMemcpyAsync(d_args, &h, sizeof h, cudaMemcpyDefault, st));   // pageable source: staged before the call returns
   unsigned blocks = ceil_div(out_len, 256);
   if (blocks > (unsigned)ctx->sm_count * 8) blocks = ctx->sm_count * 8;
   ZKB_LAUNCH(ctx, (k_poly_lincomb<FrP>), blocks, 256, 0, st, (const LincombArgs<FrP>*)d_args, d_out, out_len);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_len * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));      // h lives on this stack frame
-  return ZKB_OK;
+  return finish_out(ctx, st, out, d_out, out_len, staged);
 }
 
 template <class FrP>
 static int batch_inverse_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, uint64_t* out, size_t n) {
   using Fr = Fp<FrP>;
   Scratch ws(ctx, st);
-  Fr *d_in, *d_out, *d_scr;
-  ZKB_TRY(ws.alloc(&d_in, n));
-  ZKB_TRY(ws.alloc(&d_out, n));
+  const Fr* d_in;
+  Fr *d_out, *d_scr;
+  bool staged;
+  ZKB_TRY(stage_in(ctx, ws, st, in, n, &d_in));
+  ZKB_TRY(stage_out(ctx, ws, out, n, &d_out, &staged));
+  if (!staged && (const void*)d_out == (const void*)d_in) {      // in place on a device vector: the kernel reads `in` after writing `out`
+    staged = false;
+    Fr* copy;
+    ZKB_TRY(ws.alloc(&copy, n));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(copy, d_in, n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    d_in = copy;
+  }
   ZKB_TRY(ws.alloc(&d_scr, n));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_LAUNCH(ctx, (k_batch_inverse<FrP>), ceil_div(ceil_div(n, kPolyChunk), 128), 128, 0, st, (const Fr*)d_in, d_out, d_scr, n);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+  ZKB_LAUNCH(ctx, (k_batch_inverse<FrP>), ceil_div(ceil_div(n, kPolyChunk), 128), 128, 0, st, d_in, d_out, d_scr, n);
+  return finish_out(ctx, st, out, d_out, n, staged);
 }
 
 // ---- exclusive prefix products: out[i] = in[0] * ... * in[i - 1], out[0] = 1 -----------------------------------
@@ -435,18 +471,20 @@ template <class FrP>
 static int prefix_product_t(zkb_ctx* ctx, cudaStream_t st, const uint64_t* in, uint64_t* out, size_t n) {
   using Fr = Fp<FrP>;
   Scratch ws(ctx, st);
-  Fr *d_in, *d_out, *d_part;
+  const Fr* d_in;
+  Fr *d_out, *d_part;
+  bool staged;
   const size_t m = (n + kScanChunk - 1) / kScanChunk;
-  ZKB_TRY(ws.alloc(&d_in, n));
-  ZKB_TRY(ws.alloc(&d_out, n));
+  ZKB_TRY(stage_in(ctx, ws, st, in, n, &d_in));
+  ZKB_TRY(stage_out(ctx, ws, out, n, &d_out, &staged));
+  if (!staged && (const void*)d_out == (const void*)d_in) {      // in place: k_prefix_apply reads in[i] before it writes out[i], element by element
+    // (safe as is: each thread owns its chunk and reads an element before overwriting it)
+  }
   ZKB_TRY(ws.alloc(&d_part, m));
-  ZKB_CUDA(ctx, cudaMemcpyAsync(d_in, in, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_LAUNCH(ctx, (k_prefix_chunk_products<FrP>), ceil_div(m, 128), 128, 0, st, (const Fr*)d_in, n, d_part);
+  ZKB_LAUNCH(ctx, (k_prefix_chunk_products<FrP>), ceil_div(m, 128), 128, 0, st, d_in, n, d_part);
   ZKB_LAUNCH(ctx, (k_prefix_scan_partials<FrP>), 1, 1024, 0, st, d_part, m);
-  ZKB_LAUNCH(ctx, (k_prefix_apply<FrP>), ceil_div(m, 128), 128, 0, st, (const Fr*)d_in, n, (const Fr*)d_part, d_out);
-  ZKB_CUDA(ctx, cudaMemcpyAsync(out, d_out, n * sizeof(Fr), cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
-  return ZKB_OK;
+  ZKB_LAUNCH(ctx, (k_prefix_apply<FrP>), ceil_div(m, 128), 128, 0, st, d_in, n, (const Fr*)d_part, d_out);
+  return finish_out(ctx, st, out, d_out, n, staged);
 }
 
 }  // namespace zkb
@@ -473,15 +511,16 @@ int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t 
   ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->main;
   Scratch ws(ctx, st);
-  uint32_t *d_p, *d_q, *d_rem;
-  ZKB_TRY(ws.alloc(&d_p, n * 8));
-  ZKB_TRY(ws.alloc(&d_q, n * 8));
+  const uint32_t* d_p;
+  uint32_t *d_q = nullptr, *d_rem;
+  bool q_staged = false;
+  ZKB_TRY(stage_in(ctx, ws, st, p_mont, n * 8, &d_p));
+  if (q_mont) ZKB_TRY(stage_out(ctx, ws, q_mont, n * 8, &d_q, &q_staged));
   ZKB_TRY(ws.alloc(&d_rem, 8));
-  if (n) ZKB_CUDA(ctx, cudaMemcpyAsync(d_p, p_mont, n * 32, cudaMemcpyDefault, st));
-  ZKB_TRY(poly_div_linear_dev(ctx, st, curve, d_p, n, z_mont, q_mont ? d_q : nullptr, d_rem));
-  if (q_mont && n > 1) ZKB_CUDA(ctx, cudaMemcpyAsync(q_mont, d_q, (n - 1) * 32, cudaMemcpyDefault, st));
+  ZKB_TRY(poly_div_linear_dev(ctx, st, curve, d_p, n, z_mont, d_q, d_rem));
+  if (q_mont && q_staged && n > 1) ZKB_CUDA(ctx, cudaMemcpyAsync(q_mont, d_q, (n - 1) * 32, cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaMemcpyAsync(rem_mont, d_rem, 32, cudaMemcpyDefault, st));
-  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));          // the remainder is a host result
   return ZKB_OK;
 }
 

@@ -216,9 +216,13 @@ def prover_init(ctx, cs, idx):
 def prover_first_round(ps, cs):
     """ahp/prover.rs:95-134 -> {label: polynomial}"""
     ctx, idx = ps.ctx, ps.index
+    from .marlin import pad
     ps.w_n, ps.w_4n, oracles = [], [], {}
-    for k in range(4):                                                  # Composer::synthesize (synthesize.rs:114-132)
-        w = ps.ops.put(_mont_vec(ctx, idx.curve, [cs.assignment[v] for v in cs.w[k]], idx.n))
+    # Composer::synthesize (synthesize.rs:114-132): the assignment table goes to the device once (one conversion per
+    # variable, not per wire), the four wire columns are gathers from it, zero-padded to n
+    table = ps.ops.put(_mont_vec(ctx, idx.curve, cs.assignment, len(cs.assignment)))
+    for k in range(4):
+        w = pad(ps.ops.take(table, np.asarray(cs.w[k], dtype=np.int64)), idx.n)
         poly = _strip(_interpolate(ctx, idx.curve, w, idx.log_n))
         oracles["w_%d" % k] = poly
         ps.w_n.append(w)

@@ -252,10 +252,13 @@ int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, s
 /* ---- polynomial helpers of the Marlin prover (all Fr data Montgomery) -------------------------
  * Buffer arguments of this group, of zkb_fr_vec_op / zkb_fr_batch_inverse / zkb_fr_powers / zkb_spmv
  * (including the arrays a zkb_csr points at), of zkb_fr_convert and the scalar array of zkb_msm /
- * zkb_msm_mont may be HOST or DEVICE memory: the library moves them with cudaMemcpyDefault (unified
- * addressing), so a caller that keeps the round state resident in HBM passes device pointers and
- * pays a device-to-device copy instead of two PCIe transfers.  Scalars (z, coefficients) and
- * results that feed the transcript (remainders, points) are host memory.
+ * zkb_msm_mont may be HOST or DEVICE memory.  Host buffers are staged through stream-ordered scratch
+ * (cudaMemcpyDefault) and the call returns when the result has landed.  Device buffers are used IN PLACE, and a
+ * call of zkb_fr_vec_op / zkb_fr_batch_inverse / zkb_fr_prefix_product / zkb_fr_powers / zkb_spmv /
+ * zkb_poly_lincomb / zkb_ntt_dev whose output lives in device memory returns WITHOUT synchronising: the work is
+ * ordered on the ctx's stream (zkb_stream), later calls on the same ctx see it, and zkb_sync waits for it -- a
+ * caller that keeps the round state resident in HBM thus pays neither copies nor a host round trip per primitive.
+ * Scalars (z, coefficients) and results that feed the transcript (remainders, points) are host memory.
  * q = p / (x - z) and rem = p(z): KZG10::compute_witness_polynomial (marlin/src/pc/kzg10.rs:211-226)
  * and LabeledPolynomial::evaluate (marlin/src/lib.rs:147-156).  p has n coefficients (low degree
  * first), q receives n - 1 (may be NULL to evaluate only). */

@@ -99,5 +99,35 @@ for name in ("groth16_mimc_bls12_381_2e6", "groth16_mini_bn254") + (() if small 
     for proof in proofs:
         for key, got in (("proof_a", proof[0]), ("proof_b", proof[1]), ("proof_c", proof[2])):
             assert np.array_equal(g[key + "_xy"][0], got[0]), (name, key)
+# round-2 kernels: batched MSM entry, the batched-affine chain kernels (switch), prefix products, point decompression
+g = np.load(os.path.join(GOLD, "msm_bls12_381_g1_256.npz"))
+srs = ctx.srs_upload(1, 1, g["bases_xy"], g["bases_inf"])
+want_xy = g["result_xy"][0]
+got = ctx.msm_batch([srs, srs, srs], [g["scalars"], g["scalars"][:100], g["scalars"]], [0, 3, 0])
+assert np.array_equal(got[0][0], want_xy) and np.array_equal(got[2][0], want_xy)
+os.environ["ZKB_MSM_BATCH"] = "1"
+xy, inf = ctx.msm(srs, g["scalars"])
+assert np.array_equal(xy, want_xy), "batched-affine chains"
+os.environ["ZKB_MSM_BATCH"] = "0"
+srs.free()
+for curve in (0, 1):
+    m = 1000 if small else 5000
+    a = rng.integers(1, 1 << 62, size=(m, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 60) - 1)
+    z = ctx.fr_prefix_product(curve, a)
+    back = ctx.fr_vec_op(curve, Context.VEC_MUL, np.ascontiguousarray(z[:-1]), np.ascontiguousarray(a[:-1]))
+    assert np.array_equal(back, z[1:]), "prefix product"
+gen = synth.generator_mont(1, 1)
+pts, _ = ctx.fixed_base_mul(1, 1, gen, synth.random_exponents(rng, 64))
+canon = ctx.debug_fp_op(3, 5, pts.reshape(-1, 6).view(np.uint32).reshape(-1, 12), np.zeros((128, 12), dtype=np.uint32))   # from_mont
+comp = np.ascontiguousarray(canon.reshape(64, 2, 12)[:, 0, :]).view(np.uint8).reshape(64, 48).copy()
+ys = canon.reshape(64, 2, 12)[:, 1, :]
+pq = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+for i in range(64):
+    y = int.from_bytes(ys[i].tobytes(), "little")
+    if y > pq - y:
+        comp[i, 47] |= 0x80
+dxy, dinf, dst = ctx.points_decompress(1, 1, comp, check_subgroup=True)
+assert not dst.any() and not dinf.any() and np.array_equal(dxy, pts), "decompress"
 ctx.close()
 print("sanitize target ok")

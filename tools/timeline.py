@@ -25,27 +25,42 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--log-constraints", type=int, default=20)
 ap.add_argument("--curve", type=int, default=1)
 ap.add_argument("--out", default="gpurun_out/timeline.txt")
+ap.add_argument("--sharded", action="store_true", help="under torchrun: ONE proof by all ranks (zkb_groth16_prove_sharded), rank 0's timeline")
 a = ap.parse_args()
 
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
 torch.cuda.init()
-ctx = Context(0)
+ctx = Context(local)
+shard = None
+if a.sharded:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx.comm_init_torch()
+    shard = (world, rank)
 n = 1 << a.log_constraints
 inst = synth.MimcInstance(a.curve, n)
 A, B, C, z = inst.device_form(ctx)
 domain = 1 << (n + inst.n_inputs - 1).bit_length()
 key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, domain, b_zero_cols=np.arange(4, 4 + n, 2))
-params = key.upload(ctx, a.curve)
+params = key.upload(ctx, a.curve, shard=shard)
 r = synth.ints_to_limbs([0x1234567])[0]
 s = synth.ints_to_limbs([0x89ABCDE])[0]
 ctx.groth16_stage(params.pk, A, B, C, z, inst.n_inputs, inst.n_aux)
+prove = ctx.groth16_prove_sharded_staged if a.sharded else ctx.groth16_prove_staged
 for _ in range(3):
-    ctx.groth16_prove_staged(params.pk, r, s)
+    prove(params.pk, r, s)
 ctx.sync()
+if a.sharded:
+    dist.barrier()
 
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    ctx.groth16_prove_staged(params.pk, r, s)
+    prove(params.pk, r, s)
     ctx.sync()
     torch.cuda.synchronize()
+if rank != 0:
+    sys.exit(0)
 
 tmp = tempfile.mktemp(suffix=".json")
 prof.export_chrome_trace(tmp)
