@@ -425,6 +425,31 @@ k_seg_sum(const XYZZ<F>* __restrict__ in, size_t in_set_stride, XYZZ<F>* __restr
   }
   st_vec(&out[(size_t)blockIdx.y * n_out + o], acc);
 }
+// The same pass for BOTH axes of the bucket matrix in one launch (blockIdx.z = axis): the row sums and the column sums
+// are independent chains of latency-bound passes (~17 us per dependent G1 addition, ~55 us for G2), so running them side
+// by side halves the serial depth of the reduction.  An axis that is already done has n_out == 0.
+template <class F>
+struct SegPass {
+  const XYZZ<F>* in;
+  size_t in_set_stride;
+  XYZZ<F>* out;
+  uint32_t n_out, inner, inner_stride, outer_stride, step, K;
+};
+template <class F>
+__global__ void __launch_bounds__(128)
+k_seg_sum2(SegPass<F> pa, SegPass<F> pb) {
+  const SegPass<F>& p = blockIdx.z ? pb : pa;
+  uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= p.n_out) return;
+  const XYZZ<F>* src = p.in + (size_t)blockIdx.y * p.in_set_stride + (size_t)(o / p.inner) * p.outer_stride +
+                       (size_t)(o % p.inner) * p.inner_stride;
+  XYZZ<F> acc = ld_vec_rw(src);
+  for (uint32_t k = 1; k < p.K; k++) {
+    XYZZ<F> q = ld_vec_rw(src + (size_t)k * p.step);
+    pt_add(acc, q);
+  }
+  st_vec(&p.out[(size_t)blockIdx.y * p.n_out + o], acc);
+}
 // weighted[set][i] = (i * L) * rows[set][i] for i < H;  weighted[set][H + j] = (j + 1) * cols[set][j] for j < L
 template <class F>
 __global__ void __launch_bounds__(128)
@@ -555,6 +580,12 @@ inline int msm_pick_c(size_t n, int precomp, int scalar_bits) {
     if (!precomp) cost += (double)W * c * 9.0;      // doubling chain of the window combine (negligible)
     if (cost < best) { best = cost; best_c = c; }
   }
+  // Mid-size MSMs over window tables (the shards of a sharded proof, Marlin's commitments): the model above picks
+  // c = 16 for 2^15 <= n <= 2^19, but one thread per bucket then has only 2^15 threads -- less than one wave of the
+  // machine -- walking lists of 100+ entries.  Measured (BLS12-381, ms per MSM, c = 16 / 20; profiles/r2u_window_sweep.txt):
+  // G1 2^17 2.39 / 2.20, 2^18 3.38 / 2.83, 2^19 5.44 / 4.15; G2 2^17 8.22 / 7.34, 2^18 11.39 / 9.59 (2^16: 6.11 / 6.36).
+  // Widths whose top window is narrow (17, 18, 19 for 255 bits) are worse than both.
+  if (precomp && n >= (size_t(1) << 17) && best_c < 20) best_c = 20;
   if (const char* e = getenv(precomp ? "ZKB_MSM_C" : "ZKB_MSM_C_NOPRE")) {
     int v = atoi(e);
     if (v >= 2 && v <= 23) best_c = v;
@@ -922,8 +953,37 @@ struct MsmEngine {
       }
       return ZKB_OK;
     };
-    ZKB_TRY(reduce_axis(true, rows));
-    ZKB_TRY(reduce_axis(false, cols));
+    static const int fused_axes = []() { const char* e = getenv("ZKB_REDUCE_FUSED"); return e ? atoi(e) : 1; }();
+    if (fused_axes && lo_bits >= 2) {
+      // both axes side by side: pass i sums 4 (the last pass of an axis 2 when its bit count is odd) along each axis
+      Pt *tmp_c, *tmp_d;
+      ZKB_TRY(ws.alloc(&tmp_c, (size_t)g.n_sets * (g.B / 4 + 1)));
+      ZKB_TRY(ws.alloc(&tmp_d, (size_t)g.n_sets * (g.B / 16 + 1)));
+      struct Axis { uint32_t len, other; const Pt* in; size_t in_set_stride; Pt* bufs[2]; Pt* final_out; int flip; bool rows; };
+      Axis ax[2] = {{L, H, bucket_acc, g.B, {tmp_a, tmp_b}, rows, 0, true}, {H, L, bucket_acc, g.B, {tmp_c, tmp_d}, cols, 0, false}};
+      while (ax[0].len > 1 || ax[1].len > 1) {
+        SegPass<F> ps[2];
+        unsigned blocks = 1;
+        for (int z = 0; z < 2; z++) {
+          Axis& a = ax[z];
+          SegPass<F>& sp = ps[z];
+          memset(&sp, 0, sizeof sp);
+          if (a.len <= 1) continue;                       // this axis is done: n_out == 0
+          const uint32_t K = a.len >= 4 ? 4u : a.len;
+          const uint32_t new_len = a.len / K, n_out = new_len * a.other;
+          Pt* out = new_len == 1 ? a.final_out : a.bufs[a.flip];
+          sp.in = a.in; sp.in_set_stride = a.in_set_stride; sp.out = out; sp.n_out = n_out; sp.K = K;
+          if (a.rows) { sp.inner = new_len; sp.inner_stride = K; sp.outer_stride = a.len; sp.step = 1u; }
+          else { sp.inner = a.other; sp.inner_stride = 1u; sp.outer_stride = K * a.other; sp.step = a.other; }
+          a.in = out; a.in_set_stride = n_out; a.len = new_len; a.flip ^= 1;
+          if (ceil_div(n_out, 128) > blocks) blocks = ceil_div(n_out, 128);
+        }
+        ZKB_LAUNCH(ctx, (k_seg_sum2<F>), dim3(blocks, g.n_sets, 2), 128, 0, st, ps[0], ps[1]);
+      }
+    } else {
+      ZKB_TRY(reduce_axis(true, rows));
+      ZKB_TRY(reduce_axis(false, cols));
+    }
     ZKB_LAUNCH(ctx, (k_weight_rows_cols<F>), dim3(ceil_div(H + L, 128), g.n_sets), 128, 0, st, (const Pt*)rows,
                (const Pt*)cols, H, L, weighted);
     uint32_t n_per = H + L;
