@@ -66,7 +66,17 @@ class Composer:
     def alloc_and_assign(self, value):
         self.variable_map.append([])
         self.assignment.append(int(value) % self.p)
+        self._limbs = None
         return len(self.assignment) - 1
+
+    def witness_limbs(self):
+        """(assignment as canonical uint64[n_vars, 4], the four wire columns as int64 index arrays), built once per
+        circuit state: the reference's Composer holds field elements from `alloc_and_assign` on (composer/mod.rs:71-76),
+        so this conversion is not part of its `prove` either"""
+        if getattr(self, "_limbs", None) is None or self._limbs[2] != self.n:
+            self._limbs = (ints_to_limbs(self.assignment), [np.asarray(c, dtype=np.int64) for c in self.w], self.n,
+                           ints_to_limbs(self.pi) if self.pi else np.zeros((0, 4), dtype=np.uint64))
+        return self._limbs
 
     def create_poly_gate(self, l, r, o, aux, q_m, q_c, pi):           # arithmetic.rs:5-44
         p = self.p
@@ -208,7 +218,11 @@ def prover_init(ctx, cs, idx):
     ps = ProverState()
     ps.ctx, ps.index = ctx, idx
     ps.ops = Ops(ctx, idx.curve, idx.resident)      # resident: released by prove(); round-level callers call ps.ops.release()
-    pi_poly = _strip(_interpolate(ctx, idx.curve, ps.ops.put(_mont_vec(ctx, idx.curve, cs.public_inputs(), idx.n)), idx.log_n))
+    pi_canon = cs.witness_limbs()[3] if hasattr(cs, "witness_limbs") else ints_to_limbs(cs.public_inputs())
+    pi_n = np.zeros((idx.n, 4), dtype=np.uint64)
+    if len(pi_canon):
+        pi_n[:len(pi_canon)] = ctx.fr_convert(idx.curve, pi_canon, to_mont=True)
+    pi_poly = _strip(_interpolate(ctx, idx.curve, ps.ops.put(pi_n), idx.log_n))
     ps.pi_4n = _coset_fft_4n(ctx, idx.curve, pi_poly, idx.log_4n)
     return ps
 
@@ -220,9 +234,10 @@ def prover_first_round(ps, cs):
     ps.w_n, ps.w_4n, oracles = [], [], {}
     # Composer::synthesize (synthesize.rs:114-132): the assignment table goes to the device once (one conversion per
     # variable, not per wire), the four wire columns are gathers from it, zero-padded to n
-    table = ps.ops.put(_mont_vec(ctx, idx.curve, cs.assignment, len(cs.assignment)))
+    canon, wires = cs.witness_limbs()[:2] if hasattr(cs, "witness_limbs") else (ints_to_limbs(cs.assignment), [np.asarray(c, dtype=np.int64) for c in cs.w])
+    table = ps.ops.put(ctx.fr_convert(idx.curve, canon, to_mont=True))
     for k in range(4):
-        w = pad(ps.ops.take(table, np.asarray(cs.w[k], dtype=np.int64)), idx.n)
+        w = pad(ps.ops.take(table, wires[k]), idx.n)
         poly = _strip(_interpolate(ctx, idx.curve, w, idx.log_n))
         oracles["w_%d" % k] = poly
         ps.w_n.append(w)
@@ -457,7 +472,9 @@ def prove(ctx, pk, cs, fs_rng=None):
     idx, ck, curve = pk.index, pk.ck, pk.index.curve
     p = FR_MODULUS[curve]
     if fs_rng is None:
-        fs_rng = FiatShamirRng(b"PLONK" + b"".join(fr_to_bytes(x) for x in cs.public_inputs()), curve)
+        pi_bytes = (cs.witness_limbs()[3].tobytes() if hasattr(cs, "witness_limbs")          # canonical LE, 32 bytes each
+                    else b"".join(fr_to_bytes(x) for x in cs.public_inputs()))
+        fs_rng = FiatShamirRng(b"PLONK" + pi_bytes, curve)
     ps = prover_init(ctx, cs, idx)
     try:
         polys = dict(idx.polys)
