@@ -119,6 +119,54 @@ impl Context {
         self.check(unsafe { zkb_ntt(self.raw, curve as c_int, data_mont.as_mut_ptr(), n.trailing_zeros(), flags) })
     }
 
+    /// k independent MSMs in one call (`zkb_msm_batch`): the commitment loops of `PC::commit`
+    /// (marlin/src/pc/mod.rs:42-69) and of the `Curve::vartime_multiscalar_mul` consumers
+    /// (spartan/src/commitments.rs:42-56).  jobs[i] = (bases, base_offset, scalars as words); all bases of one call
+    /// belong to the same curve and group.  Returns (x || y limbs, is_identity) per job, in order.
+    pub fn msm_batch(&self, jobs: &[(&Srs<'_>, usize, &[u64])], scalars_mont: bool) -> Result<Vec<(Vec<u64>, bool)>> {
+        if jobs.is_empty() {
+            return Ok(Vec::new());
+        }
+        let words = jobs[0].0.words;
+        let srs: Vec<*const zkb_srs> = jobs.iter().map(|j| j.0.raw as *const zkb_srs).collect();
+        let offs: Vec<usize> = jobs.iter().map(|j| j.1).collect();
+        let ptrs: Vec<*const u64> = jobs.iter().map(|j| j.2.as_ptr()).collect();
+        let lens: Vec<usize> = jobs.iter().map(|j| j.2.len() / 4).collect();
+        let mut xy = vec![0u64; words * jobs.len()];
+        let mut inf = vec![0u8; jobs.len()];
+        self.check(unsafe {
+            zkb_msm_batch(self.raw, jobs.len(), srs.as_ptr(), offs.as_ptr(), ptrs.as_ptr(), lens.as_ptr(),
+                          scalars_mont as c_int, xy.as_mut_ptr(), inf.as_mut_ptr())
+        })?;
+        Ok(xy.chunks(words).zip(inf.iter()).map(|(p, &i)| (p.to_vec(), i != 0)).collect())
+    }
+
+    /// ark-serialize compressed points -> x || y Montgomery limbs + infinity bytes (`zkb_points_decompress`): what
+    /// `Parameters::<E>::deserialize` does per point (groth16/src/lib.rs:81, cli/src/zkp_prove.rs:117-124), with the
+    /// square roots on the device.  A status other than 0 is `SerializationError::InvalidData` for that point.
+    pub fn points_decompress(&self, curve: Curve, g2: bool, compressed: &[u8], check_subgroup: bool)
+                             -> Result<(Vec<u64>, Vec<u8>, Vec<u8>)> {
+        let words = if g2 { curve.g2_words() } else { curve.g1_words() };
+        let bytes_per_point = words * 4;
+        assert_eq!(compressed.len() % bytes_per_point, 0, "compressed points are half an affine point each");
+        let n = compressed.len() / bytes_per_point;
+        let (mut xy, mut inf, mut status) = (vec![0u64; n * words], vec![0u8; n], vec![0u8; n]);
+        let flags = if check_subgroup { ZKB_DECOMPRESS_CHECK_SUBGROUP } else { 0 };
+        self.check(unsafe {
+            zkb_points_decompress(self.raw, curve as c_int, if g2 { ZKB_G2 } else { ZKB_G1 }, compressed.as_ptr(), n, flags,
+                                  xy.as_mut_ptr(), inf.as_mut_ptr(), status.as_mut_ptr())
+        })?;
+        Ok((xy, inf, status))
+    }
+
+    /// out[i] = in[0] * ... * in[i - 1], out[0] = 1 (`zkb_fr_prefix_product`): the accumulator z of PLONK's
+    /// permutation argument (plonk/src/ahp/indexer/permutation.rs:111-118).
+    pub fn fr_prefix_product(&self, curve: Curve, in_mont: &[u64]) -> Result<Vec<u64>> {
+        let mut out = vec![0u64; in_mont.len()];
+        self.check(unsafe { zkb_fr_prefix_product(self.raw, curve as c_int, in_mont.as_ptr(), out.as_mut_ptr(), in_mont.len() / 4) })?;
+        Ok(out)
+    }
+
     /// `R1CStoQAP::witness_map` + the `into_repr` sweep of prover.rs:161: h in canonical form.
     pub fn groth16_h(&self, curve: Curve, a: &Csr<'_>, b: &Csr<'_>, c: &Csr<'_>, z_mont: &[u64], n_inputs: usize,
                      n_aux: usize) -> Result<Vec<u64>> {
