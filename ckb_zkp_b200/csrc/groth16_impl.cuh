@@ -445,9 +445,19 @@ struct Groth16Impl {
     // after the last bucket reduction only the five additions and the inversion of proof.c remain.
     ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
     for (int i = 1; i <= 5; i++) ZKB_CUDA(ctx, cudaStreamWaitEvent(side[i], ctx->ev_fork, 0));
-    ZKB_TRY(g2->msm_run(ctx, side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2));
-    ZKB_TRY(g1->msm_run(ctx, side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a));
-    ZKB_TRY(g1->msm_run(ctx, side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1));
+    // sorts of all four assignment MSMs first, their accumulations after: a sort launched behind another MSM's
+    // accumulation kernel would wait for its thousands of pending blocks (msm.cuh run_split)
+    std::function<int()> acc_b2, acc_a, acc_b1, acc_l;
+    static const int sorts_first = []() { const char* e = getenv("ZKB_SORTS_FIRST"); return e ? atoi(e) : 1; }();
+    ZKB_TRY(g2->msm_run_split(ctx, side[1], pk->b_g2, 1, zr, clamp(n_assign, pk->b_g2, 1), 0, &res->msm_b2, sorts_first ? &acc_b2 : nullptr));
+    ZKB_TRY(g1->msm_run_split(ctx, side[2], pk->a, 1, zr, clamp(n_assign, pk->a, 1), 0, &res->msm_a, sorts_first ? &acc_a : nullptr));
+    ZKB_TRY(g1->msm_run_split(ctx, side[4], pk->b_g1, 1, zr, clamp(n_assign, pk->b_g1, 1), 0, &res->msm_b1, sorts_first ? &acc_b1 : nullptr));
+    if (sorts_first) {
+      ZKB_TRY(g1->msm_run_split(ctx, side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l, &acc_l));
+      ZKB_TRY(acc_b2());
+      ZKB_TRY(acc_a());
+      ZKB_TRY(acc_b1());
+    }
     for (int i : {0, 1, 2, 4}) {
       ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
       ZKB_CUDA(ctx, cudaStreamWaitEvent(side[5], ctx->ev_join[i], 0));
@@ -464,7 +474,8 @@ struct Groth16Impl {
     }
     ZKB_TRY(compute_h(ctx, st));
     ZKB_TRY(g1->msm_run(ctx, st, pk->h, 0, (const uint32_t*)s->va.p, clamp(s->N, pk->h, 0), 0, &res->msm_h));
-    ZKB_TRY(g1->msm_run(ctx, side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
+    if (sorts_first) ZKB_TRY(acc_l());
+    else ZKB_TRY(g1->msm_run(ctx, side[3], pk->l, 0, zr + (s->n_inputs - 1) * Fr::N, clamp(s->n_aux, pk->l, 0), 0, &res->msm_l));
     for (int i : {3, 5}) {
       ZKB_CUDA(ctx, cudaEventRecord(ctx->ev_join[i], side[i]));
       ZKB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join[i], 0));

@@ -86,7 +86,7 @@ struct GroupImpl {
     return ZKB_OK;
   }
   static const GroupOps* ops() {
-    static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host,
+    static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host, &E::run_split,
                                &fixed_base_mul, &fold, &decompress, &to_affine};
     return &o;
   }

@@ -19,6 +19,9 @@
 //
 // Entry layout (uint32): bit 31 = negate, bits 0..30 = index into the base table.
 #pragma once
+#include <functional>
+#include <memory>
+
 #include "common.cuh"
 #include "curve.cuh"
 #include "devutil.cuh"
@@ -676,6 +679,16 @@ struct MsmEngine {
   // d_result: one XYZZ point (device).  All work is enqueued on `st`.
   static int run(zkb_ctx* ctx, cudaStream_t st, const zkb_srs* srs, size_t base_offset, const uint32_t* d_scalars,
                  size_t n, int scalars_mont, void* d_result_v) {
+    return run_split(ctx, st, srs, base_offset, d_scalars, n, scalars_mont, d_result_v, nullptr);
+  }
+  // Two-phase form: with `deferred` != nullptr only the sort (digits, counting sort, bucket schedule) is enqueued now and
+  // *deferred receives the closure that enqueues the accumulation and the bucket reduction.  A caller that runs several
+  // MSMs on several streams enqueues all the sorts first: kernels are dispatched roughly in launch order, so a sort
+  // launched after another MSM's accumulation kernel waits behind its thousands of pending blocks (the 2.5 ms "sort
+  // phase" after the G2 accumulation in the round-2 proof timeline).
+  static int run_split(zkb_ctx* ctx, cudaStream_t st, const zkb_srs* srs, size_t base_offset, const uint32_t* d_scalars,
+                       size_t n, int scalars_mont, void* d_result_v, std::function<int()>* deferred) {
+    if (deferred) *deferred = []() -> int { return ZKB_OK; };
     Pt* d_result = (Pt*)d_result_v;
     if (base_offset + n > srs->n) return set_err(ctx, ZKB_E_INVALID, "msm: base range out of bounds");
     if (n == 0) {
@@ -719,7 +732,8 @@ struct MsmEngine {
     const size_t max_entries = n * (size_t)g.W;
     if (max_entries >= (size_t(1) << 32)) return set_err(ctx, ZKB_E_INVALID, "msm: too many entries");
 
-    Scratch ws(ctx, st);
+    auto wsp = std::make_shared<Scratch>(ctx, st);       // lives until the deferred phase has been enqueued
+    Scratch& ws = *wsp;
     uint32_t *offsets, *cursor, *tile_sums, *entries;
     const uint32_t n_tiles = ceil_div(n_buckets, kScanTile);
     ZKB_TRY(ws.alloc(&offsets, (size_t)n_buckets + 1));
@@ -861,6 +875,8 @@ struct MsmEngine {
         lists = seg[lvl];
       }
     }
+    auto phase2 = [=]() -> int {
+    Scratch& ws = *wsp;
     // the accumulation kernel fills the machine: it goes to the low-priority bulk stream (common.cuh)
     ZKB_TRY(on_bulk_stream(ctx, st, [&](cudaStream_t bs) -> int {
       using FC = typename CallVariant<F>::type;
@@ -1002,6 +1018,12 @@ struct MsmEngine {
       ZKB_CUDA(ctx, cudaMemcpyAsync(d_result, pin, sizeof(Pt), cudaMemcpyDeviceToDevice, st));
     }
     return ZKB_OK;
+    };   // phase2
+    if (deferred) {
+      *deferred = phase2;
+      return ZKB_OK;
+    }
+    return phase2();
   }
 
   // MSM with host output (affine canonical)
@@ -1032,6 +1054,9 @@ struct GroupOps {
   int (*srs_build)(zkb_ctx*, zkb_srs*, const void*, const uint8_t*, unsigned);
   int (*msm_run)(zkb_ctx*, cudaStream_t, const zkb_srs*, size_t, const uint32_t*, size_t, int, void*);
   int (*msm_to_host)(zkb_ctx*, const zkb_srs*, size_t, const uint32_t*, size_t, int, uint64_t*, uint8_t*);
+  // msm_run in two phases: enqueues the sort now, *deferred enqueues accumulation + reduction when called
+  int (*msm_run_split)(zkb_ctx*, cudaStream_t, const zkb_srs*, size_t, const uint32_t*, size_t, int, void*,
+                       std::function<int()>* deferred);
   // out = k * P for `count` (scalar, point) pairs, one thread each (small counts: proof assembly)
   int (*fixed_base_mul)(zkb_ctx*, cudaStream_t, const void* d_base_affine, const uint32_t* d_scalars, size_t n,
                         void* d_out_affine, uint8_t* d_out_inf);
