@@ -134,7 +134,7 @@ struct XYZZ {
   ZKB_HD Affine<F> to_affine() const {
     if (is_inf()) return Affine<F>::inf();
     // 1/ZZZ gives both: 1/ZZ = ZZ^2 / ZZZ^2 ... cheaper: one inversion of ZZ*ZZZ
-    F zi = F::inv(F::mul(ZZ, ZZZ));        // 1/(ZZ*ZZZ)
+    F zi = F::inv_fast(F::mul(ZZ, ZZZ));   // 1/(ZZ*ZZZ): division-step inversion (field.cuh), ~5x shorter than the Euclid one
     F zz_inv = F::mul(zi, ZZZ);            // 1/ZZ
     F zzz_inv = F::mul(zi, ZZ);            // 1/ZZZ
     return {F::mul(X, zz_inv), F::mul(Y, zzz_inv)};

@@ -154,3 +154,28 @@ def test_points_decompress_matches_oracle(ctx, cid, group):
         assert st1[0] == 0 and H.array_point(cid, group, xy1[0], inf1[0]) == P
         _, inf2, st2 = ctx.points_decompress(cid, group, one, check_subgroup=True)
         assert st2[0] == 3 and inf2[0] == 1
+
+
+@pytest.mark.gpu
+def test_round2_entry_points_accept_empty_and_reject_bad_arguments(ctx):
+    """empty inputs are no-ops, malformed ones are ZKB_E_INVALID with a message (never a crash)"""
+    from ckb_zkp_b200 import _lib
+    from ckb_zkp_b200.backend import ZkbError
+    xy, inf, st = ctx.points_decompress(BLS12_381, 1, np.zeros((0, 48), dtype=np.uint8))
+    assert xy.shape == (0, 12) and inf.shape == (0,) and st.shape == (0,)
+    assert ctx.fr_prefix_product(BN254, np.zeros((0, 4), dtype=np.uint64)).shape == (0, 4)
+    one = H.fr_array(BN254, [7])
+    assert H.fr_ints(BN254, ctx.fr_prefix_product(BN254, one)) == [1]            # out[0] = 1 whatever the input
+    assert ctx.msm_batch([], []) == []
+    g1 = H.points_array(BN254, 1, H.multiples(BN254, 1, 4))
+    g2 = H.points_array(BN254, 2, H.multiples(BN254, 2, 4))
+    s1, s2 = ctx.srs_upload(BN254, 1, *g1), ctx.srs_upload(BN254, 2, *g2)
+    sc = H.fr_array(BN254, [1, 2, 3, 4])
+    with pytest.raises(ZkbError):                                             # mixed groups in one batch
+        ctx.msm_batch([s1, s2], [sc, sc])
+    got = ctx.msm_batch([s1], [sc[:0]])                                          # zero scalars: the identity
+    assert got[0][1] is True
+    rc = ctx.lib.zkb_points_decompress(ctx.handle, 7, 1, None, 1, 0, None, None, None)
+    assert rc == _lib.E_INVALID
+    s1.free()
+    s2.free()
