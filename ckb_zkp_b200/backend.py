@@ -337,6 +337,25 @@ class Context:
                                                    _ptr(status)))
         return xy, inf, status
 
+    def multi_pairing(self, curve, g1, g2, group_size):
+        """products of pairings (zkb_multi_pairing): g1 = (xy uint64[n, words], inf uint8[n] or None), g2 likewise,
+        n = n_groups * group_size -> uint64[n_groups, 12 * limbs] (Fq12, Montgomery, ark-ff tower order)"""
+        (xy1, inf1), (xy2, inf2) = g1, g2
+        w1, w2 = point_words(curve, 1), point_words(curve, 2)
+        xy1 = np.ascontiguousarray(xy1, dtype=np.uint64).reshape(-1, w1)
+        xy2 = np.ascontiguousarray(xy2, dtype=np.uint64).reshape(-1, w2)
+        n = xy1.shape[0]
+        if xy2.shape[0] != n or group_size < 1 or n % group_size:
+            raise ValueError("multi_pairing: %d G1 points, %d G2 points, groups of %d" % (n, xy2.shape[0], group_size))
+        inf1 = None if inf1 is None else np.ascontiguousarray(inf1, dtype=np.uint8)
+        inf2 = None if inf2 is None else np.ascontiguousarray(inf2, dtype=np.uint8)
+        if (inf1 is not None and inf1.shape != (n,)) or (inf2 is not None and inf2.shape != (n,)):
+            raise ValueError("multi_pairing: one identity flag per point")
+        out = np.zeros((n // group_size, 6 * w1), dtype=np.uint64)
+        self._check(self.lib.zkb_multi_pairing(self.handle, curve, _ptr(xy1), None if inf1 is None else _ptr(inf1), _ptr(xy2),
+                                               None if inf2 is None else _ptr(inf2), n // group_size, group_size, _ptr(out)))
+        return out
+
     # -- NTT ----------------------------------------------------------------------------------
     def ntt(self, curve, data, log_n, inverse=False, coset=False):
         """In-place transform of uint64[2^log_n, 4] (Montgomery), natural order in and out."""

@@ -1,8 +1,9 @@
-"""The prover side of the reference's KZG10 polynomial commitment (`zkp_marlin::pc`) on the B200
-backend: same structure, argument meaning and error behaviour as
+"""The reference's KZG10 polynomial commitment (`zkp_marlin::pc`) on the B200 backend: same structure, argument meaning
+and error behaviour as
 
     KZG10::commit / KZG10::open          marlin/src/pc/kzg10.rs:100-156
     PC::commit / PC::open / batch_open   marlin/src/pc/mod.rs:34-160
+    KZG10::check, PC::check / batch_check   kzg10.rs:158-173, pc/mod.rs:102-121,163-240 (pairings on the GPU, batched)
     CommitterKey, LabeledPolynomial, Randomness   marlin/src/pc/data_structures.rs:59-100,146-263
 
 The committer key lives in HBM (`powers_of_g`, `powers_of_gamma_g` uploaded once); commitments and
@@ -14,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from .backend import is_dev, point_words, torch
-from .r1cs import ints_to_limbs
+from .r1cs import ints_to_limbs, limbs_to_int
 
 FR_MODULUS = {
     _lib.BLS12_381: 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
@@ -314,3 +315,99 @@ def pc_batch_open(ck, polynomials, query_set, opening_challenge, randomnesses):
             rands.append(by_label[label][1])
         proofs.append(pc_open(ck, polys, ck.to_mont([point])[0], opening_challenge, rands))
     return proofs
+
+
+# ------------------------------------------------------------------------------------------------
+# verifier side: KZG10::check (kzg10.rs:158-173), PC::check / batch_check (pc/mod.rs:102-121,163-202)
+# ------------------------------------------------------------------------------------------------
+class MissingEvaluation(KzgError):
+    pass
+
+
+def _lincomb_points(ctx, curve, group, jobs):
+    """[sum_i k_i * P_i] for jobs = [([(xy, is_identity)], [canonical int])]: throw-away base sets, one batched MSM call"""
+    if not jobs:
+        return []
+    srs = []
+    try:
+        for pts, _ in jobs:
+            srs.append(ctx.srs_upload(curve, group, np.stack([np.asarray(p[0], dtype=np.uint64).reshape(-1) for p in pts]),
+                                      np.array([1 if p[1] else 0 for p in pts], dtype=np.uint8), precompute=False))
+        mod = FR_MODULUS[curve]
+        return ctx.msm_batch(srs, [ints_to_limbs([k % mod for k in ks]) for _, ks in jobs])
+    finally:
+        for s in srs:
+            s.free()
+
+
+def _check_many(ctx, vk, items):
+    """items: [(terms, point, proof)] with terms = [(G1 point, canonical int)] summing to comm - value * g (before the
+    hiding term) -> [bool].  KZG10::check (kzg10.rs:158-173) tests e(u, h) == e(w, beta_h - point * h); here every item
+    is one group (u, h), (-w, beta_h - point * h) of a single zkb_multi_pairing call, compared with 1."""
+    from . import pairing as _pairing
+    curve = vk.curve
+    mod = FR_MODULUS[curve]
+    rinv = pow(1 << 256, -1, mod)
+    g1_jobs, g2_jobs = [], []
+    for terms, point, (w, rand_v) in items:
+        pts, ks = [t[0] for t in terms], [t[1] for t in terms]
+        if rand_v is not None:                                         # u -= gamma_g * rand_v (:166-168)
+            pts.append(vk.gamma_g)
+            ks.append(-(limbs_to_int(rand_v) * rinv % mod))
+        g1_jobs.append((pts, ks))
+        g2_jobs.append(([vk.beta_h, vk.h], [1, -point]))               # :169
+    us = _lincomb_points(ctx, curve, _lib.G1, g1_jobs)
+    vs = _lincomb_points(ctx, curve, _lib.G2, g2_jobs)
+    groups = [[(u, vk.h), (_pairing.neg_point(curve, _lib.G1, it[2][0]), v)] for u, v, it in zip(us, vs, items)]
+    one = _pairing.gt_one(curve)
+    return [bool(np.array_equal(t, one)) for t in _pairing.multi_pairing(ctx, curve, groups)]
+
+
+def kzg_check(ctx, vk, comm, point, value, proof):
+    """KZG10::check (kzg10.rs:158-173).  point, value: canonical ints; proof = (w, rand_v Montgomery limbs or None)"""
+    return _check_many(ctx, vk, [([(comm, 1), (vk.g, -value)], point, proof)])[0]
+
+
+def _accumulate(vk, commitments, degree_bounds, point, values, opening_challenge):
+    """accumulate_commitments_and_values (pc/mod.rs:204-240) as the terms of one linear combination"""
+    mod = FR_MODULUS[vk.curve]
+    terms, acc_v, ch = [], 0, 1
+    for (comm, shifted), db, v in zip(commitments, degree_bounds, values):
+        assert (db is not None) == (shifted is not None)
+        terms.append((comm, ch))
+        acc_v = (acc_v + v * ch) % mod
+        if db is not None:
+            sc = ch * opening_challenge % mod
+            terms.append((shifted, sc))
+            acc_v = (acc_v + pow(point, vk.supported_degree - db, mod) * v % mod * sc) % mod
+        ch = ch * opening_challenge % mod * opening_challenge % mod
+    terms.append((vk.g, -acc_v))
+    return terms
+
+
+def pc_check(ctx, vk, commitments, degree_bounds, point, values, proof, opening_challenge):
+    """PC::check (pc/mod.rs:102-121): commitments = [(comm, shifted or None)], values / point / challenge canonical ints"""
+    return _check_many(ctx, vk, [(_accumulate(vk, commitments, degree_bounds, point, values, opening_challenge), point, proof)])[0]
+
+
+def pc_batch_check(ctx, vk, commitments, query_set, values, proofs, opening_challenge):
+    """PC::batch_check (pc/mod.rs:163-202).  commitments: {label: ((comm, shifted or None), degree_bound)},
+    query_set: iterable of (label, point), values: {(label, point): canonical int}, proofs in increasing point order.
+    All query points' pairings run in one device call; the result is the conjunction (result &= ..., :199)."""
+    point_to_labels = {}
+    for label, point in query_set:
+        point_to_labels.setdefault(point, set()).add(label)
+    assert len(point_to_labels) == len(proofs)
+    items = []
+    for point, proof in zip(sorted(point_to_labels), proofs):
+        cs, dbs, vs = [], [], []
+        for label in sorted(point_to_labels[point]):
+            if label not in commitments:
+                raise MissingPolynomial(label)
+            if (label, point) not in values:
+                raise MissingEvaluation(label)
+            cs.append(commitments[label][0])
+            dbs.append(commitments[label][1])
+            vs.append(values[(label, point)])
+        items.append((_accumulate(vk, cs, dbs, point, vs, opening_challenge), point, proof))
+    return all(_check_many(ctx, vk, items))

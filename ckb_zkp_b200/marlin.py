@@ -747,3 +747,98 @@ def _create_random_proof(ctx, ipk, st, x, zk_rng, fs_rng, resident):
     proof.challenges = {"alpha": alpha, "eta_a": eta_a, "eta_b": eta_b, "eta_c": eta_c, "beta": beta, "gamma": gamma,
                         "opening_challenge": opening_challenge}       # not part of the reference's Proof: kept for the tests
     return proof
+
+
+# ------------------------------------------------------------------------------------------------
+# verifier (lib.rs:183-260; ahp/verifier.rs): scalar work on the host as in the reference, the pairings of
+# PC::batch_check on the GPU in one call
+# ------------------------------------------------------------------------------------------------
+class NonSquareMatrix(Exception):
+    """ahp::Error::NonSquareMatrix (ahp/verifier.rs:44-46)"""
+
+
+def _bivariate_eval(f, size, x, y):
+    """arithmetic.rs:19-26: (v_H(x) - v_H(y)) / (x - y)"""
+    p = f.p
+    if x != y:
+        return (f.vanishing_at(size, x) - f.vanishing_at(size, y)) * pow((x - y) % p, -1, p) % p
+    return size * pow(x, size - 1, p) % p
+
+
+def verifier_equality_check(curve, index_info, public_input, ev, alpha, eta_a, eta_b, eta_c, beta, gamma):
+    """AHP::verifier_equality_check (ahp/verifier.rs:128-209).  public_input and the evaluations ev[(label, point)] are
+    canonical ints."""
+    f = Field(curve)
+    p = f.p
+    nv, nc, nnz = index_info
+    h_size, k_size = domain_size(nc), domain_size(nnz)
+    vha, vhb = f.vanishing_at(h_size, alpha), f.vanishing_at(h_size, beta)
+    r_alpha_at_beta = _bivariate_eval(f, h_size, alpha, beta)
+    formatted = [1] + [int(v) % p for v in public_input]
+    x_size = domain_size(len(formatted))
+    formatted += [0] * (x_size - len(formatted))
+    vxb = f.vanishing_at(x_size, beta)
+    # the interpolant of the formatted input over the input domain, at beta: sum_i x_i * v_X(beta) w^i / (|X| (beta - w^i))
+    w, wi, x_at_beta = f.root_of_unity(x_size), 1, 0
+    n_inv = pow(x_size, -1, p)
+    for xi in formatted:
+        if (beta - wi) % p == 0:
+            x_at_beta = xi
+            break
+        x_at_beta = (x_at_beta + xi * vxb % p * wi % p * n_inv % p * pow((beta - wi) % p, -1, p)) % p
+        wi = wi * w % p
+    za, zb = ev[("z_a", beta)], ev[("z_b", beta)]
+    lhs = (ev[("mask", beta)] + r_alpha_at_beta * (eta_a * za + eta_b * zb + eta_c * za * zb)
+           - ev[("t", beta)] * (vxb * ev[("w", beta)] + x_at_beta)) % p
+    if lhs != (ev[("h_1", beta)] * vhb + beta * ev[("g_1", beta)]) % p:                     # :163-166
+        return False
+    ab = alpha * beta % p
+    den, val = [], []
+    for name in "abc":
+        e = {k: ev[("%s_%s" % (name, k), gamma)] for k in ("row", "col", "val", "row_col")}
+        den.append((ab - alpha * e["row"] - beta * e["col"] + e["row_col"]) % p)
+        val.append(e["val"])
+    a_at = (eta_a * val[0] * den[1] * den[2] + eta_b * val[1] * den[2] * den[0] + eta_c * val[2] * den[0] * den[1]) % p
+    a_at = a_at * vha % p * vhb % p
+    b_at = den[0] * den[1] * den[2] % p
+    lhs = ev[("h_2", gamma)] * f.vanishing_at(k_size, gamma) % p
+    return lhs == (a_at - b_at * (gamma * ev[("g_2", gamma)] + ev[("t", beta)] * pow(k_size, -1, p))) % p   # :204-208
+
+
+def verify_proof(ctx, ivk, proof, public_input, fs_rng=None):
+    """zkp_marlin::verify_proof (lib.rs:183-260).  public_input: the instance without the leading one, as a Montgomery
+    uint64[n, 4] array (what create_random_proof absorbs) or canonical ints."""
+    curve = ivk.curve
+    f = Field(curve)
+    nv, nc, nnz = ivk.index_info
+    if nc != nv:
+        raise NonSquareMatrix()
+    if isinstance(public_input, np.ndarray) and public_input.ndim == 2:
+        x_mont = np.ascontiguousarray(public_input, dtype=np.uint64)
+        x_int = [f.to_int(r) for r in x_mont]
+    else:
+        x_int = [int(v) % f.p for v in public_input]
+        x_mont = f.mont_arr(x_int)
+    if fs_rng is None:
+        fs_rng = _fs.FiatShamirRng(ivk.to_bytes() + _fs.fr_mont_array_to_bytes(ctx, curve, x_mont), curve)
+    first, second, third = proof.commitments
+    h_size, k_size = domain_size(nc), domain_size(nnz)
+    fs_rng.absorb(_fs.commitments_to_bytes(curve, first))
+    alpha = sample_element_outside_domain(f, h_size, fs_rng)
+    eta_a, eta_b, eta_c = fs_rng.rand_fr(), fs_rng.rand_fr(), fs_rng.rand_fr()
+    fs_rng.absorb(_fs.commitments_to_bytes(curve, second))
+    beta = sample_element_outside_domain(f, h_size, fs_rng)
+    fs_rng.absorb(_fs.commitments_to_bytes(curve, third))
+    gamma = fs_rng.rand_fr()
+    query_set = verifier_query_set(beta, gamma)
+    fs_rng.absorb(_fs.fr_mont_array_to_bytes(ctx, curve, np.stack([to_host(e) for e in proof.evaluations])))
+    opening_challenge = fs_rng.rand_u128()
+    labels = INDEXER_POLYNOMIALS + ["w", "z_a", "z_b", "mask", "t", "g_1", "h_1", "g_2", "h_2"]      # AHP::polynomial_labels
+    bounds = dict.fromkeys(labels)
+    bounds["g_1"], bounds["g_2"] = h_size - 2, k_size - 2
+    comms = list(ivk.index_comms) + list(first) + list(second) + list(third)
+    commitments = {l: (c, bounds[l]) for l, c in zip(labels, comms)}
+    ev = {(l, pt): f.to_int(to_host(e)) for (l, pt), e in zip(query_set, proof.evaluations)}
+    if not verifier_equality_check(curve, ivk.index_info, x_int, ev, alpha, eta_a, eta_b, eta_c, beta, gamma):
+        return False
+    return _kzg.pc_batch_check(ctx, ivk.verifier_key, commitments, query_set, ev, proof.opening_proofs, opening_challenge)

@@ -245,6 +245,22 @@ int zkb_fixed_base_mul(zkb_ctx* ctx, int curve, int group, const uint64_t* base_
 int zkb_points_decompress(zkb_ctx* ctx, int curve, int group, const uint8_t* compressed, size_t n, unsigned flags,
                           uint64_t* out_xy_mont, uint8_t* out_inf, uint8_t* out_status);
 
+/* ---- batched verification: products of pairings --------------------------------------------------------------------
+ * What groth16/src/verifier.rs:18-44 (`verify_proof`: miller_loop over three pairs + final_exponentiation, compared
+ * with alpha_g1_beta_g2) and marlin/src/pc/kzg10.rs `check` / `batch_check` obtain from ark-ec's PairingEngine, for many
+ * proofs at once.  Pairs are laid out group after group: group g is pairs [g * group_size, (g + 1) * group_size) and
+ *     out_gt[g] = prod_j a(P_j, Q_j)
+ * with a = the reduced ate pairing f_{|t-1|,Q}(P)^(m (q^12 - 1) / r), m = 3 on BLS12-381 and 1 on BN254 (a fixed power
+ * of the pairing ark-ec computes: equalities between products -- all these callers test -- hold or fail identically).
+ * g1_xy / g2_xy: affine Montgomery points as everywhere in this ABI, *_inf optional identity flags (an all-zero point
+ * is the identity too; a pair with an identity contributes 1).  G2 points must be in the order-r subgroup.
+ * out_gt: n_groups x 12 x limbs(Fq) Montgomery limbs in the tower order of ark-ff's Fq12 (c0.c0.c0, c0.c0.c1, c0.c1.c0,
+ * ... c1.c2.c1; Fq6 = Fq2[v]/(v^3 - xi), Fq12 = Fq6[w]/(w^2 - v)).  One thread per pair, one per group: the call is
+ * built for batches (thousands of pairs), a single 3-pair check takes tens of milliseconds.  Host or device buffers. */
+int zkb_multi_pairing(zkb_ctx* ctx, int curve, const uint64_t* g1_xy_mont, const uint8_t* g1_inf,
+                      const uint64_t* g2_xy_mont, const uint8_t* g2_inf, size_t n_groups, size_t group_size,
+                      uint64_t* out_gt_mont);
+
 /* ---- Fr helpers (device-side batch ops on host arrays; used by the host layers) ------------ */
 /* out[i] = into_repr(in[i]) (mode 0) or from_repr(in[i]) (mode 1) */
 int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, size_t n, int mode);

@@ -12,7 +12,7 @@ LIB = os.path.join(HERE, "host_emu", "libemu.so")
 
 def build():
     deps = [SRC] + [os.path.join(HERE, "..", "ckb_zkp_b200", "csrc", f)
-                    for f in ("ptx.cuh", "field.cuh", "curve.cuh", "field_params.cuh", "serialize.cuh")]
+                    for f in ("ptx.cuh", "field.cuh", "curve.cuh", "field_params.cuh", "serialize.cuh", "pairing.cuh", "pairing_params.cuh")]
     if (not os.path.exists(LIB)) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", LIB, SRC])
     return ctypes.CDLL(LIB)

@@ -5,6 +5,7 @@
 #include <cstring>
 #include "../../ckb_zkp_b200/csrc/curve.cuh"
 #include "../../ckb_zkp_b200/csrc/serialize.cuh"
+#include "../../ckb_zkp_b200/csrc/pairing.cuh"
 
 using namespace zkb;
 
@@ -73,6 +74,30 @@ template <class F, class FrP> static int decompress_one(const uint8_t* bytes, in
   return st;
 }
 
+
+// pairing.cuh: stage 0 = Miller loop only, 1 = final exponentiation of `f_in`, 2 = both.  Points are affine Montgomery
+// limbs (G1: x,y; G2: x.c0,x.c1,y.c0,y.c1); f_in / out are 12 Fq in tower order, canonical (non-Montgomery) limbs.
+template <class PP> static void pairing_stage(int stage, const uint32_t* p, const uint32_t* q, const uint32_t* f_in, uint32_t* out) {
+  using PT = PairingT<PP>;
+  using Fq = Fp<typename PP::FqP>;
+  typename PT::F12 f, r;
+  if (stage == 1) {
+    memcpy(&f, f_in, sizeof(f));
+    Fq* e = (Fq*)&f;
+    for (int i = 0; i < 12; i++) e[i] = Fq::to_mont(e[i]);
+  } else {
+    typename PT::FC xP, yP;
+    typename PT::F2 xQ, yQ;
+    memcpy(&xP, p, sizeof(xP)); memcpy(&yP, p + Fq::N, sizeof(yP));
+    memcpy(&xQ, q, sizeof(xQ)); memcpy(&yQ, q + 2 * Fq::N, sizeof(yQ));
+    bool pi = xP.is_zero() && yP.is_zero(), qi = xQ.is_zero() && yQ.is_zero();
+    PT::miller_loop(f, xP, yP, pi, xQ, yQ, qi);
+  }
+  if (stage >= 1) { PT::final_exponentiation(r, f); f = r; }
+  PT::f12_from_mont(f);
+  memcpy(out, &f, sizeof(f));
+}
+
 extern "C" {
 // field: 0 BnFr, 1 BlsFr, 2 BnFq, 3 BlsFq, 4 BnFq2, 5 BlsFq2
 void emu_fp_op(int field, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -108,5 +133,10 @@ int emu_decompress(int curve, int group, const uint8_t* bytes, int check_subgrou
   if (curve == 1 && group == 1) return decompress_one<Fp<BlsFq>, BlsFr>(bytes, check_subgroup, out, inf);
   if (curve == 1 && group == 2) return decompress_one<Fp2<BlsFq>, BlsFr>(bytes, check_subgroup, out, inf);
   return -1;
+}
+
+void emu_pairing(int curve, int stage, const uint32_t* p, const uint32_t* q, const uint32_t* f_in, uint32_t* out) {
+  if (curve == 0) pairing_stage<BnPairing>(stage, p, q, f_in, out);
+  else pairing_stage<BlsPairing>(stage, p, q, f_in, out);
 }
 }

@@ -102,4 +102,11 @@ def test_create_random_proof_matches_oracle_and_verifies(ctx, cid, make, residen
                                     for w, rv in proof.opening_proofs]}
     assert MP.verify_proof(oivk, gpu_proof, cs.input[1:])
     assert not MP.verify_proof(oivk, gpu_proof, [(v + 1) % p for v in cs.input[1:]])
+    # and the product's own verifier (lib.rs:183-260 with the pairings of PC::batch_check on the GPU)
+    assert zm.verify_proof(ctx, ivk, proof, cs.input[1:])
+    assert zm.verify_proof(ctx, ivk, proof, H.fr_array(cid, cs.input[1:]))          # Montgomery array form of the same input
+    assert not zm.verify_proof(ctx, ivk, proof, [(v + 1) % p for v in cs.input[1:]])
+    w0, rv0 = proof.opening_proofs[0]
+    forged = zm.Proof(proof.commitments, proof.evaluations, [(proof.opening_proofs[1][0], rv0), proof.opening_proofs[1]])
+    assert not zm.verify_proof(ctx, ivk, forged, cs.input[1:])                      # equality check passes, a pairing check fails
     ipk.committer_key.free()
