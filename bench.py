@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--ref-budget-s", type=float, default=1500.0, help="wall-clock budget of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="headline only: skip the msm / ntt / sharded sub-records")
+    ap.add_argument("--verify-batch", type=int, default=8192, help="checks per zkb_multi_pairing call in the verify sub-record")
     ap.add_argument("--msm-log", type=int, default=24, help="log2 bases of the stand-alone G1 MSM (BASELINE configs[2])")
     ap.add_argument("--msm-steps", type=int, default=5)
     ap.add_argument("--ntt-logs", type=int, nargs="*", default=[21, 24])
@@ -383,6 +384,39 @@ def sub_ntt(args, torch, ctx, stream, flush, peak):
             del d, orig
     return {"metric": "fr_ntt_ms", "how": "zkb_ntt_dev in place on a resident vector, CUDA events, L2 flushed; algorithmic bytes "
                                           "= 2 * N * 32 per transform", "sizes": out}
+
+
+def sub_verify(args, ctx):
+    """batched Groth16-shaped verification (groth16/src/verifier.rs:31-41: three Miller loops and one final
+    exponentiation per proof) through zkb_multi_pairing with HOST buffers -- copies inside the timed region, wall clock
+    around the synchronous call.  Self-check on the same data: e(aP, bQ) e(-abP, Q) e(0, Q) == 1 for every group."""
+    from ckb_zkp_b200 import _lib, pairing as zpair, synth
+    from ckb_zkp_b200.r1cs import ints_to_limbs
+    out = []
+    rng = np.random.default_rng(8)
+    for curve, name in ((1, "bls12_381"), (0, "bn254")):
+        r = synth.FR_MODULUS[curve]
+        B = args.verify_batch
+        g1, g2 = synth.generator_mont(curve, _lib.G1), synth.generator_mont(curve, _lib.G2)
+        a = [int.from_bytes(rng.bytes(31), "little") % r for _ in range(B)]
+        b = [int.from_bytes(rng.bytes(31), "little") % r for _ in range(B)]
+        aP, _ = ctx.fixed_base_mul(curve, _lib.G1, g1, ints_to_limbs(a))
+        bQ, _ = ctx.fixed_base_mul(curve, _lib.G2, g2, ints_to_limbs(b))
+        nabP, _ = ctx.fixed_base_mul(curve, _lib.G1, g1, ints_to_limbs([(r - x * y % r) % r for x, y in zip(a, b)]))
+        P = np.stack([aP, nabP, np.zeros_like(aP)], axis=1).reshape(3 * B, -1)
+        Q = np.stack([bQ, np.tile(g2, (B, 1)), bQ], axis=1).reshape(3 * B, -1)
+        gt = ctx.multi_pairing(curve, (P, None), (Q, None), 3)                   # warm-up + the self-check
+        ok = bool((gt == zpair.gt_one(curve)[None, :]).all())
+        best = None
+        for _ in range(3):
+            t = time.perf_counter()
+            ctx.multi_pairing(curve, (P, None), (Q, None), 3)
+            dt = time.perf_counter() - t
+            best = dt if best is None else min(best, dt)
+        out.append({"curve": name, "checks": B, "pairs": 3 * B, "ms": best * 1e3, "checks_per_s": B / best,
+                    "pairings_per_s": 3 * B / best, "products_are_one": ok})
+    return {"metric": "groth16_shaped_pairing_checks_per_s", "how": "zkb_multi_pairing, groups of 3 pairs, host buffers in, GT out, "
+                                                                   "best of 3 wall-clock calls", "runs": out}
 
 
 class _MarlinDraws:
@@ -727,6 +761,7 @@ def run_ours(args):
             line["marlin"] = marlin_rec
             if world == 1:
                 line["ntt"] = sub_ntt(args, torch, ctx, stream, flush, peak)
+                line["verify"] = sub_verify(args, ctx)
     gpu_collectives = ctx.collective_count
     ctx.close()
     del flush

@@ -141,6 +141,24 @@ impl Context {
         Ok(xy.chunks(words).zip(inf.iter()).map(|(p, &i)| (p.to_vec(), i != 0)).collect())
     }
 
+    /// Products of pairings for MANY checks in one call (`zkb_multi_pairing`): group g = pairs
+    /// [g * group_size, (g + 1) * group_size) and the result holds one GT element (12 Fq, Montgomery, ark-ff tower order)
+    /// per group -- what `verify_proof` (groth16/src/verifier.rs:31-41: `E::miller_loop` over three pairs, then
+    /// `E::final_exponentiation`) and `KZG10::check` (marlin/src/pc/kzg10.rs:170-172) compute one check at a time.
+    /// The values are a fixed power of ark-ec's: compare them only with other outputs of this call (or with one).
+    pub fn multi_pairing(&self, curve: Curve, g1_xy: &[u64], g2_xy: &[u64], group_size: usize) -> Result<Vec<u64>> {
+        let (w1, w2) = (curve.g1_words(), curve.g2_words());
+        assert!(group_size > 0 && g1_xy.len() % w1 == 0 && g2_xy.len() % w2 == 0, "whole points, non-empty groups");
+        let n = g1_xy.len() / w1;
+        assert!(g2_xy.len() / w2 == n && n % group_size == 0, "one G2 point per G1 point, whole groups");
+        let mut gt = vec![0u64; (n / group_size) * 6 * w1];
+        self.check(unsafe {
+            zkb_multi_pairing(self.raw, curve as c_int, g1_xy.as_ptr(), std::ptr::null(), g2_xy.as_ptr(), std::ptr::null(),
+                              n / group_size, group_size, gt.as_mut_ptr())
+        })?;
+        Ok(gt)
+    }
+
     /// ark-serialize compressed points -> x || y Montgomery limbs + infinity bytes (`zkb_points_decompress`): what
     /// `Parameters::<E>::deserialize` does per point (groth16/src/lib.rs:81, cli/src/zkp_prove.rs:117-124), with the
     /// square roots on the device.  A status other than 0 is `SerializationError::InvalidData` for that point.

@@ -2,6 +2,7 @@
 // The Groth16 entry points live in groth16_api.cu.  Device code only -- there is no CPU
 // fallback: without a usable CUDA device zkb_init fails with ZKB_E_NO_DEVICE.
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "groth16.cuh"
@@ -20,6 +21,9 @@ const GroupOps* group_ops(int curve, int group) {
   if (curve == ZKB_BLS12_381) return group == ZKB_G1 ? group_ops_bls_g1() : group == ZKB_G2 ? group_ops_bls_g2() : nullptr;
   return nullptr;
 }
+
+// zkb_msm_batch takes the thread-per-term path when a call holds at least this many MSMs, each this short
+constexpr size_t kSmallBatchMinJobs = 32, kSmallBatchMaxTerms = 16;
 
 // out[i] = into_repr(in[i]) (mode 0) / from_repr(in[i]) (mode 1)
 template <class FrP>
@@ -255,7 +259,10 @@ int zkb_msm_batch(zkb_ctx* ctx, size_t k, const zkb_srs* const* srs, const size_
   if (!ctx || (k && (!srs || !base_offsets || !scalars || !n || !out_xy || !out_inf))) return ZKB_E_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (k == 0) return ZKB_OK;
-  if (k > 4096) return set_err(ctx, ZKB_E_INVALID, "msm_batch: too many MSMs in one call");
+  if (k > (size_t(1) << 20)) return set_err(ctx, ZKB_E_INVALID, "msm_batch: too many MSMs in one call");
+  bool small = k >= kSmallBatchMinJobs;
+  for (size_t i = 0; i < k && small; i++) small = n[i] <= kSmallBatchMaxTerms;
+  if (!small && k > 4096) return set_err(ctx, ZKB_E_INVALID, "msm_batch: more than 4096 MSMs that are not all short");
   for (size_t i = 0; i < k; i++) {
     if (!srs[i] || (n[i] && !scalars[i])) return set_err(ctx, ZKB_E_INVALID, "msm_batch: null argument for MSM %zu", i);
     if (srs[i]->ctx != ctx) return set_err(ctx, ZKB_E_INVALID, "msm_batch: srs belongs to another context");
@@ -270,6 +277,56 @@ int zkb_msm_batch(zkb_ctx* ctx, size_t k, const zkb_srs* const* srs, const size_
   ZKB_TRY(ws.alloc(&d_pts, k * ops->xyzz_bytes));
   ZKB_TRY(ws.alloc(&d_aff, k * ops->affine_bytes));
   ZKB_TRY(ws.alloc(&d_inf, k));
+  if (small) {
+    // thousands of 2..16-term MSMs (a batch verifier's g_ic): scalars gathered into ONE staging buffer and one copy,
+    // one thread per term, one per sum (group_impl.cuh) -- the bucket pipeline has nothing to amortise at this size
+    std::vector<SmallMsmJob> jobs(k);
+    std::vector<uint32_t> term_job;
+    std::vector<uint64_t> stage;
+    uint32_t n_terms = 0;
+    for (size_t i = 0; i < k; i++) {
+      size_t avail = base_offsets[i] <= srs[i]->n ? srs[i]->n - base_offsets[i] : 0;
+      uint32_t len = (uint32_t)(n[i] < avail ? n[i] : avail);
+      jobs[i] = SmallMsmJob{srs[i]->table, srs[i]->inf, nullptr, (uint32_t)base_offsets[i], len, n_terms, 0};
+      n_terms += len;
+    }
+    term_job.resize(n_terms);
+    stage.resize((size_t)n_terms * 4);
+    uint32_t* d_scalars;
+    ZKB_TRY(ws.alloc(&d_scalars, (size_t)n_terms * 8 + 8));
+    std::vector<char> on_dev(k, 0);
+    bool any_host = false;
+    for (size_t i = 0; i < k; i++) {
+      const uint32_t len = jobs[i].len, t0 = jobs[i].term0;
+      for (uint32_t j = 0; j < len; j++) term_job[t0 + j] = (uint32_t)i;
+      jobs[i].scalars = d_scalars + (size_t)t0 * 8;
+      if (!len) continue;
+      cudaPointerAttributes attr;
+      on_dev[i] = cudaPointerGetAttributes(&attr, scalars[i]) == cudaSuccess &&
+                  (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+      cudaGetLastError();
+      if (!on_dev[i]) { memcpy(stage.data() + (size_t)t0 * 4, scalars[i], (size_t)len * 32); any_host = true; }
+    }
+    // host scalars travel in one copy of the staging buffer; device-resident ones are then copied over their slots
+    if (any_host && n_terms) ZKB_CUDA(ctx, cudaMemcpyAsync(d_scalars, stage.data(), (size_t)n_terms * 32, cudaMemcpyDefault, st));
+    for (size_t i = 0; i < k; i++)
+      if (on_dev[i])
+        ZKB_CUDA(ctx, cudaMemcpyAsync(d_scalars + (size_t)jobs[i].term0 * 8, scalars[i], (size_t)jobs[i].len * 32, cudaMemcpyDefault, st));
+    SmallMsmJob* d_jobs;
+    uint32_t* d_term_job;
+    uint8_t* d_terms;
+    ZKB_TRY(ws.alloc(&d_jobs, k));
+    ZKB_TRY(ws.alloc(&d_term_job, (size_t)n_terms + 1));
+    ZKB_TRY(ws.alloc(&d_terms, (size_t)n_terms * ops->xyzz_bytes + 16));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), k * sizeof(SmallMsmJob), cudaMemcpyDefault, st));
+    if (n_terms) ZKB_CUDA(ctx, cudaMemcpyAsync(d_term_job, term_job.data(), (size_t)n_terms * 4, cudaMemcpyDefault, st));
+    ZKB_TRY(ops->small_msms(ctx, st, d_jobs, (uint32_t)k, d_term_job, n_terms, scalars_mont, d_terms, d_pts));
+    ZKB_TRY(ops->to_affine(ctx, st, d_pts, k, d_aff, d_inf));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out_xy, d_aff, k * ops->affine_bytes, cudaMemcpyDefault, st));
+    ZKB_CUDA(ctx, cudaMemcpyAsync(out_inf, d_inf, k, cudaMemcpyDefault, st));
+    ZKB_CUDA(ctx, cudaStreamSynchronize(st));         // also keeps jobs / term_job / stage alive until the copies ran
+    return ZKB_OK;
+  }
   // scalar copies on the main stream (stream-ordered scratch), the MSMs fan out over the side streams
   std::vector<uint32_t*> d_sc(k, nullptr);
   std::vector<size_t> len(k, 0);

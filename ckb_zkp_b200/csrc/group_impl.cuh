@@ -56,6 +56,39 @@ k_decompress(const uint8_t* __restrict__ in, uint32_t n, int check_subgroup, Aff
   out_status[i] = st;
 }
 
+// zkb_msm_batch over MANY tiny MSMs (thousands of 2..16-term sums: the g_ic of a batch verifier, verifier.rs:27-30):
+// the bucket method has nothing to amortise there, so one thread multiplies one (scalar, base) term by double-and-add
+// and one thread per MSM adds its terms.
+template <class F, class FrP>
+__global__ void __launch_bounds__(64)
+k_small_msm_batch_terms(const SmallMsmJob* __restrict__ jobs, const uint32_t* __restrict__ term_job, uint32_t n_terms,
+                        int scalars_mont, XYZZ<F>* __restrict__ terms) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_terms) return;
+  const SmallMsmJob job = jobs[term_job[t]];
+  const uint32_t j = t - job.term0;
+  XYZZ<F> r = XYZZ<F>::inf();
+  if (!job.inf[job.base_offset + j]) {
+    Fp<FrP> sc = ld_vec(reinterpret_cast<const Fp<FrP>*>(job.scalars) + j);
+    if (scalars_mont) sc = Fp<FrP>::from_mont(sc);
+    Affine<F> p = ld_vec(reinterpret_cast<const Affine<F>*>(job.table) + job.base_offset + j);   // window 0 of a table = the base
+    r = XYZZ<F>::mul_limbs(XYZZ<F>::from_affine(p), sc.v, kScalarLimbs);
+  }
+  st_vec(&terms[t], r);
+}
+
+template <class F>
+__global__ void __launch_bounds__(64)
+k_small_msm_batch_sum(const SmallMsmJob* __restrict__ jobs, uint32_t n_jobs, const XYZZ<F>* __restrict__ terms,
+                      XYZZ<F>* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_jobs) return;
+  const SmallMsmJob job = jobs[i];
+  XYZZ<F> acc = XYZZ<F>::inf();
+  for (uint32_t j = 0; j < job.len; j++) pt_add(acc, ld_vec(&terms[job.term0 + j]));
+  st_vec(&out[i], acc);
+}
+
 template <class F, class FrP>
 struct GroupImpl {
   using E = MsmEngine<F, FrP>;
@@ -85,9 +118,18 @@ struct GroupImpl {
     ZKB_LAUNCH(ctx, (k_to_affine<F>), ceil_div(n, 32), 32, 0, st, (const XYZZ<F>*)d_points, (uint32_t)n, (Affine<F>*)d_xy, d_inf);
     return ZKB_OK;
   }
+  static int small_msms(zkb_ctx* ctx, cudaStream_t st, const SmallMsmJob* d_jobs, uint32_t n_jobs, const uint32_t* d_term_job,
+                        uint32_t n_terms, int scalars_mont, void* d_terms, void* d_out) {
+    if (n_terms)
+      ZKB_LAUNCH(ctx, (k_small_msm_batch_terms<F, FrP>), ceil_div(n_terms, 64), 64, 0, st, d_jobs, d_term_job, n_terms,
+                 scalars_mont, (XYZZ<F>*)d_terms);
+    ZKB_LAUNCH(ctx, (k_small_msm_batch_sum<F>), ceil_div(n_jobs, 64), 64, 0, st, d_jobs, n_jobs, (const XYZZ<F>*)d_terms,
+               (XYZZ<F>*)d_out);
+    return ZKB_OK;
+  }
   static const GroupOps* ops() {
     static const GroupOps o = {sizeof(Affine<F>), sizeof(XYZZ<F>), &E::srs_build, &E::run, &E::run_to_host, &E::run_split,
-                               &fixed_base_mul, &fold, &decompress, &to_affine};
+                               &fixed_base_mul, &fold, &decompress, &to_affine, &small_msms};
     return &o;
   }
 };

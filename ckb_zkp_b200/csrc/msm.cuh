@@ -1049,6 +1049,15 @@ struct MsmEngine {
 // ------------------------------------------------------------------------------------------
 // type-erased per-(curve, group) operations (one translation unit each, see group_*.cu)
 // ------------------------------------------------------------------------------------------
+// one MSM of a small-batch call (zkb_msm_batch with many short MSMs): bases table[base_offset ..], canonical or
+// Montgomery scalars (device), its terms occupy [term0, term0 + len) of the scratch
+struct SmallMsmJob {
+  const void* table;
+  const uint8_t* inf;
+  const uint32_t* scalars;
+  uint32_t base_offset, len, term0, pad;
+};
+
 struct GroupOps {
   size_t affine_bytes, xyzz_bytes;
   int (*srs_build)(zkb_ctx*, zkb_srs*, const void*, const uint8_t*, unsigned);
@@ -1069,6 +1078,9 @@ struct GroupOps {
                     uint8_t* d_out_inf, uint8_t* d_out_status);
   // n XYZZ points -> canonical affine + identity flags
   int (*to_affine)(zkb_ctx*, cudaStream_t, const void* d_points, size_t n, void* d_out_affine, uint8_t* d_out_inf);
+  // many tiny MSMs at once (a batch verifier's g_ic, one per proof): one thread per (scalar, base) term, one per sum
+  int (*small_msms)(zkb_ctx*, cudaStream_t, const SmallMsmJob* d_jobs, uint32_t n_jobs, const uint32_t* d_term_job,
+                    uint32_t n_terms, int scalars_mont, void* d_terms_scratch, void* d_out_pts);
 };
 const GroupOps* group_ops(int curve, int group);
 

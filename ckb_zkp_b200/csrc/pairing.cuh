@@ -107,13 +107,38 @@ struct PairingT {
     r.c0.a2 = F2::mul(conj(a.c0.a2), frob_const(4));
     r.c1.a2 = F2::mul(conj(a.c1.a2), frob_const(5));
   }
-  // a^|x| by square-and-multiply (64-bit parameter, top bit first)
+  // Squaring in the cyclotomic subgroup (Granger-Scott, "Faster squaring in the cyclotomic subgroup of sixth degree
+  // extensions"): three Fq4 squarings of two Fq2 products each -- 18 Fq multiplications instead of the 36 of f12_sqr.
+  // Valid after the easy part of the final exponentiation only.
+  ZKB_HD static void fq4_sqr(F2& t0, F2& t1, const F2& a, const F2& b) {   // (a + b y)^2, y^2 = xi
+    F2 ab = F2::mul(a, b);
+    t0 = F2::sub(F2::sub(F2::mul(F2::add(a, b), F2::add(mul_xi(b), a)), ab), mul_xi(ab));
+    t1 = F2::dbl(ab);
+  }
+  ZKB_HD static F2 three_t_minus_2z(const F2& t, const F2& z) { return F2::add(F2::dbl(F2::sub(t, z)), t); }
+  ZKB_HD static F2 three_t_plus_2z(const F2& t, const F2& z) { return F2::add(F2::dbl(F2::add(t, z)), t); }
+  static ZKB_NOINLINE void f12_cyclotomic_sqr(F12& r, const F12& a) {
+    F2 t0, t1, t2, t3, t4, t5;
+    fq4_sqr(t0, t1, a.c0.a0, a.c1.a1);
+    fq4_sqr(t2, t3, a.c1.a0, a.c0.a2);
+    fq4_sqr(t4, t5, a.c0.a1, a.c1.a2);
+    F12 o;
+    o.c0.a0 = three_t_minus_2z(t0, a.c0.a0);
+    o.c1.a1 = three_t_plus_2z(t1, a.c1.a1);
+    o.c1.a0 = three_t_plus_2z(mul_xi(t5), a.c1.a0);
+    o.c0.a2 = three_t_minus_2z(t4, a.c0.a2);
+    o.c0.a1 = three_t_minus_2z(t2, a.c0.a1);
+    o.c1.a2 = three_t_plus_2z(t3, a.c1.a2);
+    r = o;
+  }
+
+  // a^|x| by square-and-multiply (64-bit parameter, top bit first); a in the cyclotomic subgroup
   static ZKB_NOINLINE void f12_pow_x(F12& r, const F12& a) {
     F12 acc = a, t;
     int top = 63;
     while (!((PP::X_ABS >> top) & 1)) top--;
     for (int b = top - 1; b >= 0; b--) {
-      f12_sqr(t, acc);
+      f12_cyclotomic_sqr(t, acc);
       if ((PP::X_ABS >> b) & 1) f12_mul(acc, t, a); else acc = t;
     }
     r = acc;
@@ -191,7 +216,7 @@ struct PairingT {
       pow_x_signed(t, b); pow_x_signed(u, t);               // b^(x^2)
       f12_frob(t, b); f12_frob(c, t);                       // b^(q^2)
       f12_mul(t, u, c); f12_mul(c, t, f12_conj(b));         // ^(x^2 + q^2 - 1)
-      f12_sqr(t, f); f12_mul(u, t, f);                      // f^3
+      f12_cyclotomic_sqr(t, f); f12_mul(u, t, f);                      // f^3
       f12_mul(out, c, u);
     } else {
       F12 fp, fp2, fp3, fu, fu2, fu3, y0, y2, y3, y4, y6, t0, t1;
@@ -203,14 +228,14 @@ struct PairingT {
       f12_frob(t, fu2); f12_mul(y4, fu, t); y4 = f12_conj(y4);
       f12_frob(t, fu3); f12_mul(y6, fu3, t); y6 = f12_conj(y6);
       const F12 y1 = f12_conj(f), y5 = f12_conj(fu2);
-      f12_sqr(t0, y6); f12_mul(t, t0, y4); f12_mul(t0, t, y5);
+      f12_cyclotomic_sqr(t0, y6); f12_mul(t, t0, y4); f12_mul(t0, t, y5);
       f12_mul(t, y3, y5); f12_mul(t1, t, t0);
       f12_mul(t, t0, y2); t0 = t;
-      f12_sqr(t, t1); f12_mul(t1, t, t0);
-      f12_sqr(t, t1); t1 = t;
+      f12_cyclotomic_sqr(t, t1); f12_mul(t1, t, t0);
+      f12_cyclotomic_sqr(t, t1); t1 = t;
       f12_mul(t0, t1, y1);
       f12_mul(t, t1, y0); t1 = t;
-      f12_sqr(t, t0);
+      f12_cyclotomic_sqr(t, t0);
       f12_mul(out, t, t1);
     }
   }

@@ -112,7 +112,9 @@ int zkb_msm_dev(zkb_ctx* ctx, const zkb_srs* srs, size_t base_offset, const void
  * scalars[i][..n[i]]) (zip semantics); the k sorts, accumulations and bucket reductions run concurrently on the
  * library's side streams, the k results are converted and fetched together.  scalars[i] may be host or device memory;
  * scalars_mont selects Montgomery (into_repr fused) or canonical input for all of them.  out_xy: k affine points of
- * the respective group back to back (all SRS handles of one call must belong to the same curve and group). */
+ * the respective group back to back (all SRS handles of one call must belong to the same curve and group).
+ * k <= 4096; a call whose MSMs are ALL short (n[i] <= 16, k >= 32: the g_ic of every proof of a batch verifier,
+ * groth16/src/verifier.rs:27-30) may hold up to 2^20 of them and runs one thread per (scalar, base) term instead. */
 int zkb_msm_batch(zkb_ctx* ctx, size_t k, const zkb_srs* const* srs, const size_t* base_offsets,
                   const uint64_t* const* scalars, const size_t* n, int scalars_mont, uint64_t* out_xy, uint8_t* out_inf);
 

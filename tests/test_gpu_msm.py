@@ -232,6 +232,39 @@ def test_msm_batched_affine_forced(ctx, cid, group, batch, monkeypatch):
 
 
 @pytest.mark.parametrize("cid,group", [(BN254, 1), (BLS12_381, 2)])
+def test_msm_batch_many_short_msms(ctx, cid, group):
+    """zkb_msm_batch with many short MSMs (>= 32 MSMs of <= 16 terms: the thread-per-term path a batch verifier's g_ic
+    takes) against the oracle: lengths 0..16, offsets, a base at infinity, zero / one / r - 1 scalars, canonical and
+    Montgomery scalars, a table-backed and a plain base set, host and device-resident scalars"""
+    import torch
+    c = CURVES[(cid, group)]
+    rng = random.Random(90 + 7 * cid + group)
+    n = 40
+    pts = H.multiples(cid, group, n, start=3)
+    pts[5] = None
+    xy, inf = H.points_array(cid, group, pts)
+    srs_a = ctx.srs_upload(cid, group, xy, inf)
+    srs_b = ctx.srs_upload(cid, group, xy, inf, precompute=False)
+    jobs = []
+    for i in range(70):
+        cnt = i % 17
+        off = rng.randrange(0, n - cnt + 1)
+        ks = [rng.choice([0, 1, c.r - 1, rng.randrange(c.r), rng.randrange(c.r)]) for _ in range(cnt)]
+        jobs.append((srs_a if i % 3 else srs_b, off, ks))
+    jobs.append((srs_a, n - 2, [rng.randrange(c.r) for _ in range(9)]))              # longer than the bases left: zip semantics
+    for mont in (False, True):
+        scalars = [H.fr_array(cid, ks, mont=mont) for _, _, ks in jobs]
+        scalars[3] = torch.from_numpy(scalars[3].view(np.int64)).cuda()                # one device-resident scalar array
+        got = ctx.msm_batch([s for s, _, _ in jobs], scalars, [o for _, o, _ in jobs], mont=mont)
+        for (srs, off, ks), (gxy, ginf) in zip(jobs, got):
+            use = pts[off:off + len(ks)]
+            want = c.to_affine(msm_naive(c, use, ks[:len(use)])) if use else None
+            assert H.array_point(cid, group, gxy, ginf) == want
+    srs_a.free()
+    srs_b.free()
+
+
+@pytest.mark.parametrize("cid,group", [(BN254, 1), (BLS12_381, 2)])
 def test_msm_batch_matches_single_calls(ctx, cid, group):
     """zkb_msm_batch: k MSMs over slices of two resident SRS (different offsets and lengths, an empty one, Montgomery
     scalars) give exactly what k single zkb_msm_mont calls give, and the first one what the oracle gives."""

@@ -16,7 +16,7 @@ from ckb_zkp_b200.backend import Context  # noqa: E402
 from ckb_zkp_b200.r1cs import ints_to_limbs  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--batches", type=int, nargs="+", default=[1, 64, 1024, 8192])
+ap.add_argument("--batches", type=int, nargs="+", default=[1, 64, 1024, 8192, 32768])
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 ctx = Context(0)

@@ -129,5 +129,25 @@ for i in range(64):
         comp[i, 47] |= 0x80
 dxy, dinf, dst = ctx.points_decompress(1, 1, comp, check_subgroup=True)
 assert not dst.any() and not dinf.any() and np.array_equal(dxy, pts), "decompress"
+# pairing kernels (local-memory heavy: one thread per Miller loop / per final exponentiation) and the thread-per-term
+# path of zkb_msm_batch: e(aP, Q) e(-aP, Q) == 1 on both curves; 40 two-term MSMs against single calls
+from ckb_zkp_b200 import pairing as zpair  # noqa: E402
+for curve in (0, 1):
+    g1, g2 = synth.generator_mont(curve, 1), synth.generator_mont(curve, 2)
+    ks = synth.random_exponents(rng, 4)
+    aP, _ = ctx.fixed_base_mul(curve, 1, g1, ks)
+    bQ, _ = ctx.fixed_base_mul(curve, 2, g2, synth.random_exponents(rng, 4))
+    neg = np.stack([zpair.neg_point(curve, 1, (aP[i], False))[0] for i in range(4)])
+    gt = ctx.multi_pairing(curve, (np.stack([aP, neg], axis=1).reshape(8, -1), None), (np.repeat(bQ, 2, axis=0), None), 2)
+    assert (gt == zpair.gt_one(curve)[None, :]).all(), "pairing product"
+    single = ctx.multi_pairing(curve, (aP, None), (bQ, None), 1)
+    assert len({single[i].tobytes() for i in range(4)}) == 4 and not (single == zpair.gt_one(curve)[None, :]).all(axis=1).any()
+    srs = ctx.srs_upload(curve, 1, aP, None, precompute=False)
+    scs = [synth.random_exponents(rng, 2) for _ in range(40)]
+    many = ctx.msm_batch([srs] * 40, scs, [i % 3 for i in range(40)])
+    for i in (0, 1, 2, 39):
+        one = ctx.msm(srs, scs[i], base_offset=i % 3)
+        assert many[i][1] == one[1] and np.array_equal(many[i][0], one[0]), "short-MSM batch"
+    srs.free()
 ctx.close()
 print("sanitize target ok")
