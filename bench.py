@@ -494,6 +494,8 @@ def sub_marlin(args, torch, ctx, world, rank, barrier, tmax):
         parts = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(parts, t)
         same = all(bool(torch.equal(x, parts[0])) for x in parts)
+    # the reference's acceptance test on the last proof (zkp_marlin::verify_proof, lib.rs:183-260), pairings on the GPU
+    verified = bool(zm.verify_proof(ctx, ivk, proof, np.ascontiguousarray(circuit.arrays[3][1:]))) if rank == 0 else None
     out = {"metric": "marlin_proofs_per_sec_bn254_2e%d_constraints" % log_h, "value": 1.0 / sec, "unit": "proofs/s",
            "n_gpus": world, "scaling": "strong" if world > 1 else "weak", "steps": steps, "ms_per_proof": sec * 1e3,
            "workload": "Marlin prove, BN254, MiMC chain with %d constraints: |H| = 2^%d, |K| = 2^%d, |B| = 2^%d, committer key %d "
@@ -504,7 +506,7 @@ def sub_marlin(args, torch, ctx, world, rank, barrier, tmax):
                   "ranks, committer key sliced over them",
            "commitments": sum(len(r) for r in proof.commitments), "evaluations": len(proof.evaluations),
            "openings": len(proof.opening_proofs), "gpu_launches_per_rank": launches, "collectives_per_proof": colls,
-           "same_proof_on_every_rank": same, "setup_s": round(setup_s, 1)}
+           "same_proof_on_every_rank": same, "verified_on_gpu": verified, "setup_s": round(setup_s, 1)}
     ipk.committer_key.free()
     return out
 

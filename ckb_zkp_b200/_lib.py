@@ -88,6 +88,7 @@ SIGNATURES = {
     "zkb_multi_pairing": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "zkb_fr_convert": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int]),
     "zkb_poly_div_linear": (c_int, [c_void_p, c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
+    "zkb_poly_eval_batch": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "zkb_poly_lincomb": (c_int, [c_void_p, c_int, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "zkb_fr_prefix_product": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t]),
     "zkb_fr_batch_inverse": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t]),

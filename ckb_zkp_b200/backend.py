@@ -396,6 +396,21 @@ class Context:
     def poly_eval(self, curve, p_mont, z_mont):
         return self.poly_div_linear(curve, p_mont, z_mont, want_quotient=False)[1]
 
+    def poly_eval_batch(self, curve, polys, points_mont):
+        """[polys[j](points[j])] as uint64[k, 4] (Montgomery) with one device synchronisation (zkb_poly_eval_batch)"""
+        polys = [_fr(p, "polynomial") for p in polys]
+        k = len(polys)
+        pts = np.ascontiguousarray(points_mont, dtype=np.uint64).reshape(-1, 4)
+        if pts.shape[0] != k:
+            raise ValueError("one point per polynomial")
+        out = np.zeros((k, 4), dtype=np.uint64)
+        if k == 0:
+            return out
+        ptrs = (ctypes.c_void_p * k)(*[(p.data_ptr() if is_dev(p) else p.ctypes.data) if len(p) else None for p in polys])
+        lens = (ctypes.c_size_t * k)(*[len(p) for p in polys])
+        self._check(self.lib.zkb_poly_eval_batch(self.handle, curve, k, ptrs, lens, _ptr(pts), _ptr(out)))
+        return out
+
     def poly_lincomb(self, curve, polys, coeffs_mont, shifts=None, out_len=None):
         """sum_j coeffs[j] * x^shifts[j] * polys[j] as uint64[out_len, 4]"""
         polys = [_fr(p, "polynomial") for p in polys]

@@ -524,6 +524,31 @@ int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t 
   return ZKB_OK;
 }
 
+int zkb_poly_eval_batch(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,
+                        const uint64_t* points_mont, uint64_t* out_mont) {
+  if (!ctx || (k && (!polys_mont || !lens || !points_mont || !out_mont))) return ZKB_E_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (curve != ZKB_BN254 && curve != ZKB_BLS12_381) return set_err(ctx, ZKB_E_INVALID, "poly_eval_batch: unknown curve %d", curve);
+  if (k == 0) return ZKB_OK;
+  if (k > 4096) return set_err(ctx, ZKB_E_INVALID, "poly_eval_batch: too many polynomials in one call");
+  for (size_t j = 0; j < k; j++)
+    if (lens[j] && !polys_mont[j]) return set_err(ctx, ZKB_E_INVALID, "poly_eval_batch: null polynomial %zu", j);
+  ZKB_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->main;
+  Scratch ws(ctx, st);
+  uint32_t* d_rem;
+  ZKB_TRY(ws.alloc(&d_rem, 8 * k));
+  // the k remainder trees are enqueued back to back; ONE copy and ONE synchronisation fetch all values
+  for (size_t j = 0; j < k; j++) {
+    const uint32_t* d_p;
+    ZKB_TRY(stage_in(ctx, ws, st, polys_mont[j], lens[j] * 8, &d_p));
+    ZKB_TRY(poly_div_linear_dev(ctx, st, curve, d_p, lens[j], points_mont + 4 * j, nullptr, d_rem + 8 * j));
+  }
+  ZKB_CUDA(ctx, cudaMemcpyAsync(out_mont, d_rem, 32 * k, cudaMemcpyDefault, st));
+  ZKB_CUDA(ctx, cudaStreamSynchronize(st));
+  return ZKB_OK;
+}
+
 int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,
                      const size_t* shifts, const uint64_t* coeffs_mont, uint64_t* out_mont, size_t out_len) {
   if (!ctx || (k && (!polys_mont || !lens || !coeffs_mont)) || (out_len && !out_mont)) return ZKB_E_INVALID;

@@ -183,6 +183,25 @@ def kzg_open(ck, p, point_mont, rand):
     return w, rand_v
 
 
+def _open_job(ck, p, point_mont, rand):
+    """the checks and divisions of KZG10::open (kzg10.rs:125-156) without the MSMs: -> (jobs, rand_v); the witness is
+    the sum of the jobs' MSMs"""
+    ctx = ck.ctx
+    deg = _degree(p)
+    if deg < 1:
+        raise DegreeIsZero()
+    if deg > ck.n:
+        raise DegreeOutOfBound()
+    witness, _ = ctx.poly_div_linear(ck.curve, p, point_mont)    # compute_witness_polynomial :211-226
+    nz = _leading_zeros(witness)
+    jobs = [(ck.g, nz, witness[nz:])]
+    rand_v = None
+    if rand.is_hiding():
+        rq, rand_v = ctx.poly_div_linear(ck.curve, rand.blinding, point_mont)
+        jobs.append((ck.gamma_g, 0, rq))
+    return jobs, rand_v
+
+
 def _commit_job(ck, p, hiding_bound, rng, base_offset=0, supported_degree=None):
     """the checks and rng draws of KZG10::commit (kzg10.rs:100-123) without the MSMs: -> (jobs, Randomness) where jobs
     is [(srs, base_offset, scalars)] -- the commitment is the sum of the jobs' MSMs"""
@@ -275,8 +294,8 @@ def _pc_commit_serial(ck, polynomials, rng=None):
     return comms, rands
 
 
-def pc_open(ck, polynomials, point_mont, opening_challenge, randomnesses):
-    """PC::open (pc/mod.rs:73-100); opening_challenge is a canonical int"""
+def _open_combination(ck, polynomials, opening_challenge, randomnesses):
+    """the linear combination PC::open builds before KZG10::open (pc/mod.rs:81-98) -> (p, Randomness)"""
     ctx = ck.ctx
     mod = FR_MODULUS[ck.curve]
     polys, shifts, coeffs = [], [], []
@@ -295,6 +314,12 @@ def pc_open(ck, polynomials, point_mont, opening_challenge, randomnesses):
         challenge = challenge * opening_challenge % mod * opening_challenge % mod
     p = ctx.poly_lincomb(ck.curve, polys, ck.to_mont(coeffs), shifts)
     r = Randomness(ctx.poly_lincomb(ck.curve, rpolys, ck.to_mont(rcoeffs)) if rpolys else None)
+    return p, r
+
+
+def pc_open(ck, polynomials, point_mont, opening_challenge, randomnesses):
+    """PC::open (pc/mod.rs:73-100); opening_challenge is a canonical int"""
+    p, r = _open_combination(ck, polynomials, opening_challenge, randomnesses)
     return kzg_open(ck, p, point_mont, r)
 
 
@@ -305,7 +330,7 @@ def pc_batch_open(ck, polynomials, query_set, opening_challenge, randomnesses):
     point_to_labels = {}
     for label, point in query_set:
         point_to_labels.setdefault(point, set()).add(label)
-    proofs = []
+    groups = []
     for point in sorted(point_to_labels):
         polys, rands = [], []
         for label in sorted(point_to_labels[point]):
@@ -313,8 +338,22 @@ def pc_batch_open(ck, polynomials, query_set, opening_challenge, randomnesses):
                 raise MissingPolynomial(label)
             polys.append(by_label[label][0])
             rands.append(by_label[label][1])
-        proofs.append(pc_open(ck, polys, ck.to_mont([point])[0], opening_challenge, rands))
-    return proofs
+        groups.append((polys, rands, point))
+    if ck.shard is not None:                                        # every MSM is a collective: one by one
+        return [pc_open(ck, polys, ck.to_mont([point])[0], opening_challenge, rands) for polys, rands, point in groups]
+    # the witness MSMs of all query points go to the device together (zkb_msm_batch), like the commitments of a round
+    ctx = ck.ctx
+    jobs, slots, rand_vs = [], [], []
+    for polys, rands, point in groups:
+        p, r = _open_combination(ck, polys, opening_challenge, rands)
+        j, rand_v = _open_job(ck, p, ck.to_mont([point])[0], r)
+        slots.append(list(range(len(jobs), len(jobs) + len(j))))
+        jobs += j
+        rand_vs.append(rand_v)
+    pts = ctx.msm_batch([j[0] for j in jobs], [j[2] for j in jobs], [j[1] for j in jobs], mont=True) if jobs else []
+    multi = [idx for idx in slots if len(idx) > 1]
+    sums = iter(_add_point_groups(ctx, ck.curve, [[pts[i] for i in idx] for idx in multi]) if multi else [])
+    return [(pts[idx[0]] if len(idx) == 1 else next(sums), rv) for idx, rv in zip(slots, rand_vs)]
 
 
 # ------------------------------------------------------------------------------------------------

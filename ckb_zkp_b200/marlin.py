@@ -739,7 +739,8 @@ def _create_random_proof(ctx, ipk, st, x, zk_rng, fs_rng, resident):
     query_set = verifier_query_set(beta, gamma)
     by_label = {P.label: P for P in labeled}
     points = {beta: f.mont(beta), gamma: f.mont(gamma)}
-    evaluations = [ctx.poly_eval(curve, by_label[label].coeffs, points[pt]) for label, pt in query_set]   # lib.rs:147-156
+    evaluations = list(ctx.poly_eval_batch(curve, [by_label[label].coeffs for label, _ in query_set],
+                                           np.stack([points[pt] for _, pt in query_set])))               # lib.rs:147-156
     fs_rng.absorb(_fs.fr_mont_array_to_bytes(ctx, curve, np.stack(evaluations)))                          # lib.rs:157
     opening_challenge = fs_rng.rand_u128()                             # u128::rand(&mut fs_rng).into() (lib.rs:158)
     opening_proofs = _kzg.pc_batch_open(ck, labeled, query_set, opening_challenge, rands)                 # lib.rs:160-166

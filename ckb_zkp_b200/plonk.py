@@ -327,7 +327,8 @@ def construct_linear_combinations(ctx, idx, beta, gamma, alpha, zeta, polys):
     lcs = {l: [(1, l)] for l in ("w_0", "w_1", "w_2", "w_3", "z", "sigma_0", "sigma_1", "sigma_2", "q_arith")}
     zn = pow(zeta, idx.n, p)
     lcs["t"] = [(1, "t_0"), (zn, "t_1"), (zn * zn % p, "t_2"), (zn * zn % p * zn % p, "t_3")]
-    ev = lambda label, x: _eval(ctx, curve, polys[label], x)
+    # the prover evaluates its polynomials (ahp/evaluations.rs:24-48), the verifier reads the proof's evaluations (:50-60)
+    ev = (lambda label, x: polys[label]) if isinstance(polys.get("w_0"), int) else (lambda label, x: _eval(ctx, curve, polys[label], x))
     w = [ev("w_%d" % k, zeta) for k in range(4)]
     z_sh = ev("z", zeta * idx.group_gen % p)
     s = [ev("sigma_%d" % k, zeta) for k in range(3)]
@@ -518,3 +519,55 @@ def prove(ctx, pk, cs, fs_rng=None):
         ps.ops.release()
     proof = Proof([first_comms, second_comms, third_comms], evaluations, openings)
     return proof, {"beta": beta, "gamma": gamma, "alpha": alpha, "zeta": zeta, "epsilon": epsilon, "evals": evals}
+
+
+class _VerifierInfo:
+    """what the verifier knows of the index (ahp/verifier.rs:19-35: the domain and the coset representatives)"""
+
+    def __init__(self, curve, n, ks):
+        self.curve, self.n, self.ks, self.resident = curve, n, list(ks), False
+        self.log_n = n.bit_length() - 1
+        self.group_gen = _group_gen(curve, self.log_n)
+
+
+def verify(ctx, vk, public_inputs, proof, fs_rng=None):
+    """Plonk::verify (lib.rs:206-290): challenges re-derived from the transcript, the equality check on the evaluations,
+    then the opening checks -- the role of PC::check_combinations (:277-286): the commitment of every linear combination
+    is the same combination of the labeled commitments, one KZG check per query point with the combinations' evaluations
+    batched by powers of epsilon -- with all pairings in one device call (kzg10._check_many)."""
+    rk = vk["rk"]
+    curve = rk.curve
+    p = FR_MODULUS[curve]
+    info = _VerifierInfo(curve, vk["n"], vk["ks"])
+    public_inputs = [int(x) % p for x in public_inputs]
+    if fs_rng is None:
+        fs_rng = FiatShamirRng(b"PLONK" + b"".join(fr_to_bytes(x) for x in public_inputs), curve)
+    first, second, third = proof.commitments
+    fs_rng.absorb(_comms_to_bytes(curve, first))
+    beta, gamma = fs_rng.rand_fr(), fs_rng.rand_fr()
+    fs_rng.absorb(_comms_to_bytes(curve, second))
+    alpha = fs_rng.rand_fr()
+    fs_rng.absorb(_comms_to_bytes(curve, third))
+    zeta = fs_rng.rand_fr()
+    qs = verifier_query_set(info, zeta)
+    fs_rng.absorb(b"".join(fr_to_bytes(e) for e in proof.evaluations))
+    epsilon = fs_rng.rand_fr()
+    evals = dict(zip(sorted(qs), proof.evaluations))                     # evaluation_labels.sort_by label (lib.rs:232-244)
+    if not verifier_equality_check(ctx, info, beta, gamma, alpha, zeta, evals, public_inputs):
+        return False
+    labels = list(vk["labels"]) + list(ORACLE_LABELS)
+    comms = dict(zip(labels, [c for c, _ in list(vk["comms"]) + list(first) + list(second) + list(third)]))
+    lcs = construct_linear_combinations(ctx, info, beta, gamma, alpha, zeta, evals)
+    items = []
+    for point_label in ("shifted_zeta", "zeta"):
+        group = [label for label in sorted(qs) if qs[label][0] == point_label]
+        point = qs[group[0]][1]
+        terms, acc_v, ch = [], 0, 1
+        for label in group:                                              # accumulate_commitments_and_values over the combinations
+            terms += [(comms[poly_label], ch * coeff % p) for coeff, poly_label in lcs[label]]
+            acc_v = (acc_v + ch * evals[label]) % p
+            ch = ch * epsilon % p * epsilon % p
+        terms.append((rk.g, -acc_v))
+        items.append((terms, point, proof.openings[point_label]))
+    return all(_kzg._check_many(ctx, rk, items))
+

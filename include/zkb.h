@@ -282,6 +282,12 @@ int zkb_fr_convert(zkb_ctx* ctx, int curve, const uint64_t* in, uint64_t* out, s
  * first), q receives n - 1 (may be NULL to evaluate only). */
 int zkb_poly_div_linear(zkb_ctx* ctx, int curve, const uint64_t* p_mont, size_t n, const uint64_t z_mont[4],
                         uint64_t* q_mont, uint64_t rem_mont[4]);
+/* k polynomial evaluations in one call: out[j] = polys[j](points[j]) -- the 21 evaluations zkp_marlin's prover sends
+ * (marlin/src/lib.rs:147-156: `polynomial.evaluate(point)` in a loop over the query set).  The remainder trees are
+ * enqueued back to back; one copy and one synchronisation return all values.  points_mont / out_mont: k * 4 limbs. */
+int zkb_poly_eval_batch(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,
+                        const uint64_t* points_mont, uint64_t* out_mont);
+
 /* out[i] = sum_j coeffs[j] * polys[j][i - shifts[j]], i < out_len: the accumulation of PC::open
  * (marlin/src/pc/mod.rs:85-98; shift = supported_degree - degree_bound, :241-250).  k <= 64. */
 int zkb_poly_lincomb(zkb_ctx* ctx, int curve, size_t k, const uint64_t* const* polys_mont, const size_t* lens,

@@ -202,3 +202,26 @@ def test_kzg_commit_large(ctx):
     want, _ = ctx.fixed_base_mul(cid, 1, gen, H.ints_to_u64([qe], 4))
     assert np.array_equal(w[0], want[0])
     ck.free()
+
+
+@pytest.mark.parametrize("cid", [BN254, BLS12_381])
+def test_poly_eval_batch(ctx, cid):
+    """zkb_poly_eval_batch: lengths 0, 1, one chunk, several tree levels; host and device-resident coefficients; each
+    polynomial at its own point -- against Horner on integers and against the single-call entry"""
+    import torch
+    mod = FR[cid].p
+    rng = random.Random(17 + cid)
+    lens = [0, 1, 2, 127, 128, 129, 5000, 40000]
+    polys = [[rng.randrange(mod) for _ in range(n)] for n in lens]
+    points = [rng.randrange(mod) for _ in lens]
+    points[3] = 0
+    arrs = [H.fr_array(cid, p) for p in polys]
+    arrs[6] = torch.from_numpy(arrs[6].view(np.int64)).cuda()
+    got = ctx.poly_eval_batch(cid, arrs, H.fr_array(cid, points))
+    want = [OK.poly_eval(p, z, mod) for p, z in zip(polys, points)]
+    assert H.fr_ints(cid, got) == want
+    for j in (1, 5, 7):
+        assert np.array_equal(ctx.poly_eval(cid, arrs[j], H.fr_array(cid, [points[j]])[0]), got[j])
+    assert ctx.poly_eval_batch(cid, [], np.zeros((0, 4), dtype=np.uint64)).shape == (0, 4)
+    with pytest.raises(ValueError):
+        ctx.poly_eval_batch(cid, arrs[:2], H.fr_array(cid, points[:3]))

@@ -154,4 +154,12 @@ def test_keygen_prove_self_verifies(ctx, cid, resident):
         want = c1.mul_affine(c1.gen, kg * (P_beta - v) % p * pow(beta_t - z, -1, p) % p)
         w, rand_v = proof.openings[point_label]
         assert rand_v is None and H.array_point(cid, 1, w[0], w[1]) == want
+
+    # Plonk::verify (lib.rs:206-290) on the device: transcript re-derived, equality check, both openings by pairings
+    pis = cs.public_inputs()
+    assert zp.verify(ctx, vk, pis, proof)
+    assert not zp.verify(ctx, vk, [(pis[0] + 1) % p] + list(pis[1:]), proof)              # another transcript, check fails
+    swapped = zp.Proof(proof.commitments, proof.evaluations, {"zeta": proof.openings["shifted_zeta"],
+                                                              "shifted_zeta": proof.openings["zeta"]})
+    assert not zp.verify(ctx, vk, pis, swapped)                                         # equality check passes, pairings fail
     pk.ck.free()
