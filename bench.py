@@ -422,16 +422,33 @@ def sub_verify(args, ctx):
 class _MarlinDraws:
     """the prover's zk_rng: scalar draws, and bulk draws for the 3|H|-coefficient mask polynomial (same seed on every rank)"""
 
+    pool = None
+
     def __init__(self, seed, p):
         import random
-        self.r, self.np, self.p = random.Random(seed), np.random.default_rng(seed), p
+        self.r, self.seed, self.p = random.Random(seed), seed, p
 
     def randrange(self, *a):
         return self.r.randrange(*a)
 
     def field_array(self, count):
-        a = self.np.integers(0, np.iinfo(np.uint64).max, size=(count, 4), dtype=np.uint64, endpoint=True)
-        a[:, 3] &= np.uint64((1 << (self.p.bit_length() - 1 - 192)) - 1)        # < 2^(bits - 1) < p
+        """count residues < 2^(bits - 1) < p as uint64[count, 4], drawn by four independently seeded generators on four
+        host threads (numpy releases the GIL): the 3|H| mask coefficients are the one bulk draw of a Marlin proof"""
+        from concurrent.futures import ThreadPoolExecutor
+        a = np.empty((count, 4), dtype=np.uint64)
+        T = 4
+        per = (count + T - 1) // T
+
+        def fill(i):
+            lo, hi = i * per, min(count, (i + 1) * per)
+            if hi > lo:
+                g = np.random.Generator(np.random.SFC64([self.seed, i]))
+                a[lo:hi] = g.integers(0, np.iinfo(np.uint64).max, size=(hi - lo, 4), dtype=np.uint64, endpoint=True)
+
+        if _MarlinDraws.pool is None:
+            _MarlinDraws.pool = ThreadPoolExecutor(T)
+        list(_MarlinDraws.pool.map(fill, range(T)))
+        a[:, 3] &= np.uint64((1 << (self.p.bit_length() - 1 - 192)) - 1)
         return a
 
 

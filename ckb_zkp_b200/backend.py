@@ -33,7 +33,7 @@ class ZkbError(RuntimeError):
 
 
 def _ptr(a):
-    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    return ctypes.c_void_p(a.__array_interface__["data"][0]) if a is not None else None
 
 
 def is_dev(a):

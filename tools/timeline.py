@@ -26,6 +26,7 @@ ap.add_argument("--log-constraints", type=int, default=20)
 ap.add_argument("--curve", type=int, default=1)
 ap.add_argument("--out", default="gpurun_out/timeline.txt")
 ap.add_argument("--sharded", action="store_true", help="under torchrun: ONE proof by all ranks (zkb_groth16_prove_sharded), rank 0's timeline")
+ap.add_argument("--partial-of", type=int, default=0, help="single GPU: rank 0's share of a proof sharded over N ranks (zkb_groth16_prove_partial, no exchange)")
 a = ap.parse_args()
 
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -44,11 +45,15 @@ inst = synth.MimcInstance(a.curve, n)
 A, B, C, z = inst.device_form(ctx)
 domain = 1 << (n + inst.n_inputs - 1).bit_length()
 key = synth.SyntheticKey(inst.n_inputs + inst.n_aux, inst.n_inputs, domain, b_zero_cols=np.arange(4, 4 + n, 2))
+if a.partial_of:
+    shard = (a.partial_of, 0)
 params = key.upload(ctx, a.curve, shard=shard)
 r = synth.ints_to_limbs([0x1234567])[0]
 s = synth.ints_to_limbs([0x89ABCDE])[0]
 ctx.groth16_stage(params.pk, A, B, C, z, inst.n_inputs, inst.n_aux)
 prove = ctx.groth16_prove_sharded_staged if a.sharded else ctx.groth16_prove_staged
+if a.partial_of:
+    prove = lambda pk, r_, s_: ctx.groth16_prove_partial(pk, A, B, C, z, inst.n_inputs, inst.n_aux, r_, s_)
 for _ in range(3):
     prove(params.pk, r, s)
 ctx.sync()
