@@ -34,7 +34,20 @@ static int multi_pairing_t(zkb_ctx* ctx, const uint64_t* g1_xy, const uint8_t* g
   // 64-thread blocks: a pairing thread lives in local memory (an Fq12 is up to 576 bytes), small blocks spread a
   // modest batch over all SMs
   ZKB_LAUNCH(ctx, (k_miller_loops<PP>), ceil_div(n, 64), 64, 0, st, d_g1, d_i1, d_g2, d_i2, n, d_ml);
-  ZKB_LAUNCH(ctx, (k_pairing_finish<PP>), ceil_div(n_groups, 64), 64, 0, st, d_ml, n_groups, group_size, d_out);
+  // a long product is folded by chunks of 16 first, so that no thread multiplies more than 16 + 16 values in a row
+  const size_t kChunk = 16;
+  size_t group = group_size;
+  F12* d_cur = d_ml;
+  while (group > 2 * kChunk) {
+    const size_t n_chunks = ceil_div(group, kChunk);
+    F12* d_next;
+    ZKB_TRY(ws.alloc(&d_next, n_groups * n_chunks));
+    ZKB_LAUNCH(ctx, (k_gt_chunk_products<PP>), ceil_div(n_groups * n_chunks, 64), 64, 0, st, d_cur, n_groups, group, kChunk,
+               n_chunks, d_next);
+    d_cur = d_next;
+    group = n_chunks;
+  }
+  ZKB_LAUNCH(ctx, (k_pairing_finish<PP>), ceil_div(n_groups, 64), 64, 0, st, d_cur, n_groups, group, d_out);
   ZKB_CUDA(ctx, cudaMemcpyAsync(out_gt, d_out, n_groups * sizeof(F12), cudaMemcpyDefault, st));
   ZKB_CUDA(ctx, cudaStreamSynchronize(st));
   return ZKB_OK;

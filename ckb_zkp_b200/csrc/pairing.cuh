@@ -268,6 +268,21 @@ __global__ void __launch_bounds__(64) k_miller_loops(const Affine<Fp<typename PP
   ml[i] = f;
 }
 
+// large groups (a random-linear-combination batch check is ONE product over thousands of pairs): partial products of
+// `chunk` consecutive loop values per thread, out[g * n_chunks + c]; applied repeatedly until a group is short
+template <class PP>
+__global__ void __launch_bounds__(64) k_gt_chunk_products(const typename PairingT<PP>::F12* in, size_t n_groups, size_t group,
+                                                          size_t chunk, size_t n_chunks, typename PairingT<PP>::F12* out) {
+  using PT = PairingT<PP>;
+  size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (t >= n_groups * n_chunks) return;
+  const size_t g = t / n_chunks, c = t % n_chunks;
+  const size_t lo = c * chunk, hi = lo + chunk < group ? lo + chunk : group;
+  typename PT::F12 f = in[g * group + lo], u;
+  for (size_t j = lo + 1; j < hi; j++) { PT::f12_mul(u, f, in[g * group + j]); f = u; }
+  out[t] = f;
+}
+
 // one thread per group of `group` consecutive pairs: out[g] = final_exponentiation(prod ml[g * group + j]) (Montgomery form)
 template <class PP>
 __global__ void __launch_bounds__(64) k_pairing_finish(const typename PairingT<PP>::F12* ml, size_t n_groups, size_t group,

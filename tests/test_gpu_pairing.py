@@ -162,3 +162,24 @@ def test_kzg10_commit_open_check(ctx, cid):
             assert not zk.kzg_check(ctx, vk, prev, z, value, proof)
         prev = comm
     ck.free()
+
+
+@pytest.mark.parametrize("cid", [BN254, BLS12_381])
+def test_long_products(ctx, cid):
+    """a group much longer than a verifier's three pairs (one random-linear-combination check over a whole batch): the
+    chunked product path.  prod e(a_i G1, b_i G2) == e((sum a_i b_i) G1, G2), and == 1 when the sum vanishes mod r"""
+    g1, g2 = CURVES[(cid, 1)], CURVES[(cid, 2)]
+    rng = random.Random(5)
+    can = lambda v: H.ints_to_u64(v, 4)
+    gen1, gen2 = arr1(cid, g1.gen)[0], arr2(cid, g2.gen)[0]
+    for n in (33, 100, 700):
+        a = [rng.randrange(1, g1.r) for _ in range(n)]
+        b = [rng.randrange(1, g1.r) for _ in range(n)]
+        total = sum(x * y for x, y in zip(a, b)) % g1.r
+        aP = ctx.fixed_base_mul(cid, _lib.G1, gen1, can(a + [1]))
+        bQ = ctx.fixed_base_mul(cid, _lib.G2, gen2, can(b + [(g1.r - total) % g1.r]))
+        got = ctx.multi_pairing(cid, (aP[0][:n], None), (bQ[0][:n], None), n)
+        want = ctx.multi_pairing(cid, ctx.fixed_base_mul(cid, _lib.G1, gen1, can([total])), (gen2.reshape(1, -1), None), 1)
+        assert np.array_equal(got, want)
+        closed = ctx.multi_pairing(cid, aP, bQ, n + 1)
+        assert np.array_equal(closed[0], zp.gt_one(cid))
