@@ -34,6 +34,10 @@ struct DevCsr {
   size_t n_rows = 0, nnz = 0;
 };
 
+// The result / shard blocks of the stage are curve-typed structs (groth16_impl.cuh) but the stage outlives a change of
+// curve on the same context: both blocks are allocated at this fixed size, which either curve's layout fits
+constexpr size_t kStageBlockBytes = 32768;
+
 struct Groth16Stage {
   int curve = -1;
   size_t n_inputs = 0, n_aux = 0, n_rows = 0, N = 0;

@@ -297,6 +297,7 @@ struct Groth16Impl {
   using Res = G16Results<Fq, Fq2>;
   using Part = G16Partial<Fq, Fq2>;
   using Shard = G16Shard<Fq, Fq2>;
+  static_assert(sizeof(Res) <= kStageBlockBytes && sizeof(Shard) <= kStageBlockBytes, "stage blocks hold either curve's layout");
 
   static int ensure(zkb_ctx* ctx, DevBuf* b, size_t bytes) {
     if (b->p && b->cap >= bytes) return ZKB_OK;
@@ -357,7 +358,7 @@ struct Groth16Impl {
     ZKB_TRY(ensure(ctx, &s->vb, s->N * sizeof(Fr)));
     ZKB_TRY(ensure(ctx, &s->vc, s->N * sizeof(Fr)));
     ZKB_TRY(ensure(ctx, &s->scratch, s->N * sizeof(Fr)));
-    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, sizeof(Res)));
+    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, kStageBlockBytes));
     if (!s->scal) ZKB_CUDA(ctx, cudaMalloc(&s->scal, sizeof(Fr) * 4));
     ZKB_CUDA(ctx, cudaMemcpyAsync(s->z.p, z_mont, nz * sizeof(Fr), cudaMemcpyHostToDevice, st));
     s->pending[0] = s->pending[1] = s->pending[2] = nullptr;
@@ -515,7 +516,7 @@ struct Groth16Impl {
     for (int i = 0; i < kNumSideStreams; i++) side[i] = ctx->serial ? st : ctx->side[i];
     const GroupOps* g1 = group_ops(CURVE, ZKB_G1);
     const GroupOps* g2 = group_ops(CURVE, ZKB_G2);
-    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, sizeof(Shard)));
+    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, kStageBlockBytes));
     Res* res = (Res*)s->results;
     Shard* sh = (Shard*)s->shard;
     Fr* scal = (Fr*)s->scal;
@@ -582,9 +583,9 @@ struct Groth16Impl {
     if (!pk || pk->curve != CURVE || pk->ctx != ctx || !pk->sharded)
       return set_err(ctx, ZKB_E_INVALID, "groth16: not a sharded proving key of this context");
     if (!s) { ctx->stage = new Groth16Stage(); s = ctx->stage; }
-    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, sizeof(Res)));
+    if (!s->results) ZKB_CUDA(ctx, cudaMalloc(&s->results, kStageBlockBytes));
     if (!s->scal) ZKB_CUDA(ctx, cudaMalloc(&s->scal, sizeof(Fr) * 4));
-    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, sizeof(Shard)));
+    if (!s->shard) ZKB_CUDA(ctx, cudaMalloc(&s->shard, kStageBlockBytes));
     cudaStream_t st = ctx->main;
     Res* res = (Res*)s->results;
     Shard* sh = (Shard*)s->shard;

@@ -6,6 +6,8 @@ names: many proofs against one verifying key in one device call.
     verify_proofs(pvk, proofs, public_inputs_list)   the same test for every proof: one batched MSM call for the g_ic,
                                                      one zkb_multi_pairing call for the 3 * B Miller loops and B final
                                                      exponentiations
+    verify_proofs_batched(pvk, proofs, inputs, rng)  ONE decision for the batch by a random linear combination of the B
+                                                     equations: B + 3 Miller loops and one final exponentiation
 
     e(A, B) * e(g_ic, -gamma) * e(C, -delta) == e(alpha, beta),     g_ic = gamma_abc[0] + sum_i x_i * gamma_abc[i + 1]
 """
@@ -64,3 +66,55 @@ def verify_proofs(pvk, proofs, public_inputs_list):
 
 def verify_proof(pvk, proof, public_inputs):
     return verify_proofs(pvk, [proof], [public_inputs])[0]
+
+
+def verify_proofs_batched(pvk, proofs, public_inputs_list, rng):
+    """True iff every proof verifies, except with probability ~2^-128 over `rng` (needs getrandbits): the B equations
+    are raised to random 128-bit exponents r_i and multiplied, and bilinearity moves the exponents into G1:
+
+        prod_i e(r_i A_i, B_i) * e(sum_i r_i g_ic_i, -gamma) * e(sum_i r_i C_i, -delta) * e(-(sum_i r_i) alpha, beta) == 1
+
+    B + 3 Miller loops and ONE final exponentiation instead of 3 B and B (verifier.rs:31-43 per proof); the scalar
+    multiplications r_i A_i are one thread each (zkb_msm_batch, short-MSM path), sum r_i C_i is one MSM over the B points,
+    sum r_i g_ic_i one MSM over gamma_abc_g1 with the scalars (sum_i r_i, sum_i r_i x_i1, ...).  A False does not say
+    which proof failed: fall back to verify_proofs for that."""
+    if len(proofs) != len(public_inputs_list):
+        raise ValueError("one public-input list per proof")
+    for x in public_inputs_list:
+        if len(x) + 1 != pvk.n_gamma_abc:
+            raise MalformedVerifyingKey()
+    if not proofs:
+        return True
+    ctx, curve, vk = pvk.ctx, pvk.curve, pvk.vk
+    p = FR_MODULUS[curve]
+    B = len(proofs)
+    rs = [rng.getrandbits(128) | 1 for _ in range(B)]
+    pts = lambda which: (np.stack([np.asarray(getattr(pr, which)[0], dtype=np.uint64).reshape(-1) for pr in proofs]),
+                         np.array([1 if getattr(pr, which)[1] else 0 for pr in proofs], dtype=np.uint8))
+    a_xy, a_inf = pts("a")
+    b_xy, b_inf = pts("b")
+    c_xy, c_inf = pts("c")
+    r_limbs = ints_to_limbs(rs)
+    srs_a = ctx.srs_upload(curve, _lib.G1, a_xy, a_inf, precompute=False)
+    srs_c = ctx.srs_upload(curve, _lib.G1, c_xy, c_inf, precompute=False)
+    try:
+        if B >= 32:
+            ra = ctx.msm_batch([srs_a] * B, [r_limbs[i:i + 1] for i in range(B)], list(range(B)))     # r_i * A_i
+        else:
+            ra = [ctx.msm(srs_a, r_limbs[i:i + 1], base_offset=i) for i in range(B)]
+        c_sum = ctx.msm(srs_c, r_limbs)                                                              # sum r_i C_i
+    finally:
+        srs_a.free()
+        srs_c.free()
+    s = [sum(rs) % p] + [sum(r * (int(x[j]) % p) for r, x in zip(rs, public_inputs_list)) % p
+                         for j in range(pvk.n_gamma_abc - 1)]
+    g_ic_sum = ctx.msm(pvk.gamma_abc_srs, ints_to_limbs(s))                                          # sum r_i g_ic_i
+    alpha_xy, alpha_inf = ctx.fixed_base_mul(curve, _lib.G1, vk.alpha_g1[0], ints_to_limbs([(p - s[0]) % p]))
+    g1_xy = np.concatenate([np.stack([x[0] for x in ra]), g_ic_sum[0][None, :], c_sum[0][None, :], alpha_xy])
+    g1_inf = np.array([1 if x[1] else 0 for x in ra] + [int(g_ic_sum[1]), int(c_sum[1]), int(alpha_inf[0])], dtype=np.uint8)
+    g2_xy = np.concatenate([b_xy, np.stack([np.asarray(q[0], dtype=np.uint64).reshape(-1)
+                                            for q in (pvk.gamma_g2_neg, pvk.delta_g2_neg, vk.beta_g2)])])
+    g2_inf = np.concatenate([b_inf, np.array([int(q[1]) for q in (pvk.gamma_g2_neg, pvk.delta_g2_neg, vk.beta_g2)], dtype=np.uint8)])
+    gt = ctx.multi_pairing(curve, (g1_xy, g1_inf), (g2_xy, g2_inf), B + 3)
+    return bool(np.array_equal(gt[0], _pairing.gt_one(curve)))
+

@@ -177,5 +177,17 @@ def test_round2_entry_points_accept_empty_and_reject_bad_arguments(ctx):
     assert got[0][1] is True
     rc = ctx.lib.zkb_points_decompress(ctx.handle, 7, 1, None, 1, 0, None, None, None)
     assert rc == _lib.E_INVALID
+    # zkb_multi_pairing / zkb_poly_eval_batch: no groups is a no-op, empty groups / unknown curves / null buffers are errors
+    import ctypes
+    assert ctx.multi_pairing(BN254, (np.zeros((0, 8), dtype=np.uint64), None), (np.zeros((0, 16), dtype=np.uint64), None), 3).shape == (0, 48)
+    gt = np.zeros(48, dtype=np.uint64)
+    p1, p2 = np.ascontiguousarray(g1[0][:1]), np.ascontiguousarray(g2[0][:1])
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert ctx.lib.zkb_multi_pairing(ctx.handle, BN254, vp(p1), None, vp(p2), None, 1, 0, vp(gt)) == _lib.E_INVALID
+    assert ctx.lib.zkb_multi_pairing(ctx.handle, 9, vp(p1), None, vp(p2), None, 1, 1, vp(gt)) == _lib.E_INVALID
+    assert ctx.lib.zkb_multi_pairing(ctx.handle, BN254, None, None, vp(p2), None, 1, 1, vp(gt)) == _lib.E_INVALID
+    assert ctx.lib.zkb_multi_pairing(ctx.handle, BN254, vp(p1), None, vp(p2), None, 1, 1, vp(gt)) == 0 and gt.any()
+    assert ctx.lib.zkb_poly_eval_batch(ctx.handle, BN254, 1, None, None, None, None) == _lib.E_INVALID
+    assert ctx.lib.zkb_poly_eval_batch(ctx.handle, BN254, 0, None, None, None, None) == 0
     s1.free()
     s2.free()

@@ -223,3 +223,21 @@ def test_serial_measurement_mode_is_the_same_proof(ctx, name):
     finally:
         ctx.set_serial(False)
     assert_proof(g, ctx.groth16_prove(*args))
+
+
+def test_curve_switch_on_a_fresh_context():
+    """the stage of a context outlives a change of curve: BN254 first (the smaller result block), then BLS12-381, then
+    BN254 again on a context of its own -- every proof equal to its golden vector (regression: the result block used to
+    keep the size of the first curve proven on the context)"""
+    from ckb_zkp_b200.backend import Context
+    own = Context(0)
+    try:
+        for name in ("groth16_mini_bn254", "groth16_mimc_bls12_381_2e6", "groth16_mimc_bn254_2e10", "groth16_mini_bls12_381"):
+            g = load(name)
+            params = params_from_golden(own, g)
+            A, B, C = matrices(g)
+            proof = own.groth16_prove(params.pk, A, B, C, g["z"], int(g["n_inputs"]), int(g["n_aux"]), g["r"][0], g["s"][0])
+            assert_proof(g, proof)
+            params.free()
+    finally:
+        own.close()

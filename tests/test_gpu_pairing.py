@@ -132,6 +132,16 @@ def test_groth16_verify_proof_on_gpu(ctx, cid):
     for pr, x, g in zip(batch[:4], inputs[:4], got[:4]):
         assert OP.verify_proof(cid, opvk, (pt1(pr.a), pt2(pr.b), pt1(pr.c)), x) == g
     assert zv.verify_proofs(pvk, [], []) == []
+    # one decision for a whole batch (random linear combination of the equations): B + 3 Miller loops, one final exponentiation
+    brng = random.Random(99)
+    good = [proofs[i % 6] for i in range(40)]
+    assert zv.verify_proofs_batched(pvk, good, [[10]] * 40, brng)                      # short-MSM path (>= 32 proofs)
+    assert zv.verify_proofs_batched(pvk, good[:5], [[10]] * 5, brng)                   # one call per r_i * A_i
+    assert not zv.verify_proofs_batched(pvk, good[:17] + [bad4] + good[18:], [[10]] * 40, brng)
+    assert not zv.verify_proofs_batched(pvk, good, [[10]] * 39 + [[12]], brng)
+    assert zv.verify_proofs_batched(pvk, [], [], brng)
+    with pytest.raises(zv.MalformedVerifyingKey):
+        zv.verify_proofs_batched(pvk, good[:2], [[10], []], brng)
     pvk.free()
 
 

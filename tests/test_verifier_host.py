@@ -52,6 +52,18 @@ class MockVerifierContext:
             out.append((xy[0], bool(inf[0])))
         return out
 
+    def msm(self, srs, scalars, base_offset=0, mont=False):
+        assert not mont
+        c = CURVES[(srs.curve, srs.group)]
+        pt = c.to_affine(msm_naive(c, srs.pts[base_offset:], H.u64_to_ints(np.asarray(scalars))))
+        xy, inf = H.points_array(srs.curve, srs.group, [pt])
+        return xy[0], bool(inf[0])
+
+    def fixed_base_mul(self, curve, group, base_xy, scalars):
+        c = CURVES[(curve, group)]
+        base = H.array_point(curve, group, np.asarray(base_xy), 0)
+        return H.points_array(curve, group, [c.mul_affine(base, k) if k else None for k in H.u64_to_ints(np.asarray(scalars))])
+
     def multi_pairing(self, curve, g1, g2, group_size):
         """csrc/pairing.cuh on the host: Miller loops, product in the oracle's field, final exponentiation"""
         from oracle.pyref import pairing as OP
@@ -95,6 +107,14 @@ def test_groth16_verifier_over_mock(cid):
     bad = Proof(arr(cid, 1, c), arr(cid, 2, b), arr(cid, 1, a))
     assert zv.verify_proofs(pvk, [proof, proof, bad], [[10], [11], [10]]) == [True, False, False]
     assert zv.verify_proof(pvk, proof, [10 + p])
+    # the random-linear-combination form: one decision for the batch
+    a2, b2, c2 = OG.create_proof(pk, cs, 777, 888)
+    proof2 = Proof(arr(cid, 1, a2), arr(cid, 2, b2), arr(cid, 1, c2))
+    brng = random.Random(1)
+    assert zv.verify_proofs_batched(pvk, [proof, proof2, proof], [[10], [10], [10]], brng)
+    assert not zv.verify_proofs_batched(pvk, [proof, bad, proof2], [[10], [10], [10]], brng)
+    assert not zv.verify_proofs_batched(pvk, [proof, proof2], [[10], [11]], brng)
+    assert zv.verify_proofs_batched(pvk, [], [], brng)
     with pytest.raises(zv.MalformedVerifyingKey):
         zv.verify_proof(pvk, proof, [])
     with pytest.raises(ValueError):

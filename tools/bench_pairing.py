@@ -38,3 +38,41 @@ for curve, name in ((_lib.BN254, "bn254"), (_lib.BLS12_381, "bls12_381")):
             best = dt if best is None else min(best, dt)
         print(json.dumps({"curve": name, "groups": B, "pairs": n, "ms": round(best * 1e3, 3),
                           "verifications_per_s": round(B / best, 1), "pairings_per_s": round(n / best, 1)}), flush=True)
+
+# the two Groth16 batch verifiers of ckb_zkp_b200/verifier.py through the Python API (proof objects in, decisions out):
+# per-proof decisions (3 B Miller loops, B final exponentiations) vs one decision by random linear combination (B + 3, 1)
+import random  # noqa: E402
+
+from ckb_zkp_b200 import generator as zgen, groth16 as zg, verifier as zv  # noqa: E402
+from ckb_zkp_b200.r1cs import ONE  # noqa: E402
+
+
+class _Mini:
+    """groth16/tests/mini.rs:12-44"""
+
+    def generate_constraints(self, cs):
+        vx, vy = cs.alloc(lambda: 2), cs.alloc(lambda: 3)
+        vz = cs.alloc_input(lambda: 10)
+        for _ in range(10):
+            cs.enforce([(1, vx)], [(1, vy), (2, ONE)], [(1, vz)])
+
+
+for curve, name in ((_lib.BN254, "bn254"), (_lib.BLS12_381, "bls12_381")):
+    rng = random.Random(7)
+    data = zgen.generate_random_parameters(ctx, curve, _Mini(), rng)
+    params = data.upload(ctx)
+    base = [zg.create_random_proof(params, _Mini(), rng) for _ in range(8)]
+    params.free()
+    pvk = zv.prepare_verifying_key(ctx, curve, data.vk)
+    for B in (1024, 8192):
+        proofs = [base[i % 8] for i in range(B)]
+        inputs = [[10]] * B
+        for fn, label in ((lambda: all(zv.verify_proofs(pvk, proofs, inputs)), "each"),
+                          (lambda: zv.verify_proofs_batched(pvk, proofs, inputs, rng), "random_linear_combination")):
+            assert fn()
+            t = time.perf_counter()
+            ok = fn()
+            dt = time.perf_counter() - t
+            print(json.dumps({"curve": name, "groth16_proofs": B, "mode": label, "accepted": bool(ok), "ms": round(dt * 1e3, 2),
+                              "proofs_per_s": round(B / dt, 1)}), flush=True)
+    pvk.free()
