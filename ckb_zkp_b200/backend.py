@@ -213,6 +213,27 @@ class Context:
         self._check(self.lib.zkb_msm_batch(self.handle, k, handles, offs, ptrs, lens, 1 if mont else 0, _ptr(out), _ptr(oinf)))
         return [(out[i], bool(oinf[i])) for i in range(k)]
 
+    def msm_many(self, srs, scalars, base_offsets=None, mont=False):
+        """k MSMs of n terms each over ONE base set (zkb_msm_batch): scalars uint64[k, n, 4] on the host, MSM i reads
+        bases [base_offsets[i], base_offsets[i] + n) -> (xy uint64[k, words], inf uint8[k]).  The argument arrays are
+        built without a Python-level loop: the shape of a batch verifier's calls (thousands of short MSMs)."""
+        sc = np.ascontiguousarray(scalars, dtype=np.uint64)
+        if sc.ndim != 3 or sc.shape[2] != 4:
+            raise ValueError("scalars must be uint64[k, n, 4]")
+        k, n = sc.shape[0], sc.shape[1]
+        w = point_words(srs.curve, srs.group)
+        out = np.zeros((k, w), dtype=np.uint64)
+        oinf = np.zeros(k, dtype=np.uint8)
+        if k == 0:
+            return out, oinf
+        handles = np.full(k, srs.handle.value, dtype=np.uint64)
+        offs = np.zeros(k, dtype=np.uint64) if base_offsets is None else np.ascontiguousarray(base_offsets, dtype=np.uint64)
+        ptrs = np.uint64(sc.ctypes.data) + np.arange(k, dtype=np.uint64) * np.uint64(n * 32)
+        lens = np.full(k, n, dtype=np.uint64)
+        self._check(self.lib.zkb_msm_batch(self.handle, k, _ptr(handles), _ptr(offs), _ptr(ptrs), _ptr(lens), 1 if mont else 0,
+                                           _ptr(out), _ptr(oinf)))
+        return out, oinf
+
     def msm_dev(self, srs, d_scalars_ptr, n, base_offset=0):
         """Same with canonical scalars already in device memory (raw device pointer)."""
         out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)

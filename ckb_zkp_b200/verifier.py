@@ -45,6 +45,11 @@ def prepare_verifying_key(ctx, curve, vk):
                                 _pairing.neg_point(curve, _lib.G2, vk.delta_g2), srs)
 
 
+def _proof_arrays(proofs, which):
+    return (np.stack([np.asarray(getattr(pr, which)[0], dtype=np.uint64).reshape(-1) for pr in proofs]),
+            np.array([1 if getattr(pr, which)[1] else 0 for pr in proofs], dtype=np.uint8))
+
+
 def verify_proofs(pvk, proofs, public_inputs_list):
     """-> [bool] in order.  public inputs are canonical ints (E::Fr), one list per proof."""
     if len(proofs) != len(public_inputs_list):
@@ -56,12 +61,17 @@ def verify_proofs(pvk, proofs, public_inputs_list):
         return []
     ctx, curve = pvk.ctx, pvk.curve
     p = FR_MODULUS[curve]
-    # g_ic (verifier.rs:27-30): the MSM of gamma_abc_g1 with the scalars (1, x_1, ..., x_n)
-    scalars = [ints_to_limbs([1] + [int(v) % p for v in x]) for x in public_inputs_list]
-    g_ic = ctx.msm_batch([pvk.gamma_abc_srs] * len(proofs), scalars)
-    groups = [[(pr.a, pr.b), (g, pvk.gamma_g2_neg), (pr.c, pvk.delta_g2_neg)] for pr, g in zip(proofs, g_ic)]
-    tests = _pairing.multi_pairing(ctx, curve, groups)                    # verifier.rs:31-41
-    return [bool(np.array_equal(t, pvk.alpha_g1_beta_g2)) for t in tests]  # :43
+    B = len(proofs)
+    # g_ic (verifier.rs:27-30): the MSM of gamma_abc_g1 with the scalars (1, x_1, ..., x_n), all proofs in one call
+    scalars = ints_to_limbs([v for x in public_inputs_list for v in [1] + [int(e) % p for e in x]]).reshape(B, pvk.n_gamma_abc, 4)
+    g_xy, g_inf = ctx.msm_many(pvk.gamma_abc_srs, scalars)
+    (a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf) = (_proof_arrays(proofs, w) for w in "abc")
+    g1 = (np.stack([a_xy, g_xy, c_xy], axis=1).reshape(3 * B, -1), np.stack([a_inf, g_inf, c_inf], axis=1).reshape(-1))
+    fixed = lambda q: np.broadcast_to(np.asarray(q[0], dtype=np.uint64).reshape(1, -1), b_xy.shape)
+    g2 = (np.stack([b_xy, fixed(pvk.gamma_g2_neg), fixed(pvk.delta_g2_neg)], axis=1).reshape(3 * B, -1),
+          np.stack([b_inf, np.zeros_like(b_inf), np.zeros_like(b_inf)], axis=1).reshape(-1))
+    tests = ctx.multi_pairing(curve, g1, g2, 3)                            # verifier.rs:31-41
+    return [bool(t) for t in (tests == pvk.alpha_g1_beta_g2[None, :]).all(axis=1)]   # :43
 
 
 def verify_proof(pvk, proof, public_inputs):
@@ -75,7 +85,7 @@ def verify_proofs_batched(pvk, proofs, public_inputs_list, rng):
         prod_i e(r_i A_i, B_i) * e(sum_i r_i g_ic_i, -gamma) * e(sum_i r_i C_i, -delta) * e(-(sum_i r_i) alpha, beta) == 1
 
     B + 3 Miller loops and ONE final exponentiation instead of 3 B and B (verifier.rs:31-43 per proof); the scalar
-    multiplications r_i A_i are one thread each (zkb_msm_batch, short-MSM path), sum r_i C_i is one MSM over the B points,
+    multiplications r_i A_i are one thread each (zkb_msm_batch, short-MSM path from 32 proofs up), sum r_i C_i is one MSM over the B points,
     sum r_i g_ic_i one MSM over gamma_abc_g1 with the scalars (sum_i r_i, sum_i r_i x_i1, ...).  A False does not say
     which proof failed: fall back to verify_proofs for that."""
     if len(proofs) != len(public_inputs_list):
@@ -89,19 +99,12 @@ def verify_proofs_batched(pvk, proofs, public_inputs_list, rng):
     p = FR_MODULUS[curve]
     B = len(proofs)
     rs = [rng.getrandbits(128) | 1 for _ in range(B)]
-    pts = lambda which: (np.stack([np.asarray(getattr(pr, which)[0], dtype=np.uint64).reshape(-1) for pr in proofs]),
-                         np.array([1 if getattr(pr, which)[1] else 0 for pr in proofs], dtype=np.uint8))
-    a_xy, a_inf = pts("a")
-    b_xy, b_inf = pts("b")
-    c_xy, c_inf = pts("c")
+    (a_xy, a_inf), (b_xy, b_inf), (c_xy, c_inf) = (_proof_arrays(proofs, w) for w in "abc")
     r_limbs = ints_to_limbs(rs)
     srs_a = ctx.srs_upload(curve, _lib.G1, a_xy, a_inf, precompute=False)
     srs_c = ctx.srs_upload(curve, _lib.G1, c_xy, c_inf, precompute=False)
     try:
-        if B >= 32:
-            ra = ctx.msm_batch([srs_a] * B, [r_limbs[i:i + 1] for i in range(B)], list(range(B)))     # r_i * A_i
-        else:
-            ra = [ctx.msm(srs_a, r_limbs[i:i + 1], base_offset=i) for i in range(B)]
+        ra_xy, ra_inf = ctx.msm_many(srs_a, r_limbs.reshape(B, 1, 4), np.arange(B))                  # r_i * A_i
         c_sum = ctx.msm(srs_c, r_limbs)                                                              # sum r_i C_i
     finally:
         srs_a.free()
@@ -110,8 +113,8 @@ def verify_proofs_batched(pvk, proofs, public_inputs_list, rng):
                          for j in range(pvk.n_gamma_abc - 1)]
     g_ic_sum = ctx.msm(pvk.gamma_abc_srs, ints_to_limbs(s))                                          # sum r_i g_ic_i
     alpha_xy, alpha_inf = ctx.fixed_base_mul(curve, _lib.G1, vk.alpha_g1[0], ints_to_limbs([(p - s[0]) % p]))
-    g1_xy = np.concatenate([np.stack([x[0] for x in ra]), g_ic_sum[0][None, :], c_sum[0][None, :], alpha_xy])
-    g1_inf = np.array([1 if x[1] else 0 for x in ra] + [int(g_ic_sum[1]), int(c_sum[1]), int(alpha_inf[0])], dtype=np.uint8)
+    g1_xy = np.concatenate([ra_xy, g_ic_sum[0][None, :], c_sum[0][None, :], alpha_xy])
+    g1_inf = np.concatenate([ra_inf, np.array([int(g_ic_sum[1]), int(c_sum[1]), int(alpha_inf[0])], dtype=np.uint8)])
     g2_xy = np.concatenate([b_xy, np.stack([np.asarray(q[0], dtype=np.uint64).reshape(-1)
                                             for q in (pvk.gamma_g2_neg, pvk.delta_g2_neg, vk.beta_g2)])])
     g2_inf = np.concatenate([b_inf, np.array([int(q[1]) for q in (pvk.gamma_g2_neg, pvk.delta_g2_neg, vk.beta_g2)], dtype=np.uint8)])

@@ -52,6 +52,12 @@ class MockVerifierContext:
             out.append((xy[0], bool(inf[0])))
         return out
 
+    def msm_many(self, srs, scalars, base_offsets=None, mont=False):
+        k = len(scalars)
+        offs = [0] * k if base_offsets is None else [int(o) for o in base_offsets]
+        res = [self.msm(srs, scalars[i], base_offset=offs[i]) for i in range(k)]
+        return np.stack([r[0] for r in res]), np.array([1 if r[1] else 0 for r in res], dtype=np.uint8)
+
     def msm(self, srs, scalars, base_offset=0, mont=False):
         assert not mont
         c = CURVES[(srs.curve, srs.group)]
