@@ -41,14 +41,6 @@ def is_dev(a):
     return torch is not None and isinstance(a, torch.Tensor)
 
 
-def _addr(a):
-    """host or device address: the library copies with cudaMemcpyDefault (unified addressing), so every buffer
-    argument of the vector / polynomial / MSM entry points may live on either side"""
-    if a is None:
-        return None
-    return ctypes.c_void_p(a.data_ptr()) if is_dev(a) else _ptr(a)
-
-
 def _fr(a, what="scalars"):
     if is_dev(a):
         if a.dtype != torch.int64 or a.dim() != 2 or a.shape[1] != 4 or not a.is_cuda:
@@ -136,11 +128,41 @@ class Context:
                                "CPU fallback" % device)
         self.handle = h
         self.device = device
+        self._stream_ptr = self.lib.zkb_stream(h)
+        self._lib_stream, self._order_cur = None, None
 
     # -- plumbing -----------------------------------------------------------------------------
     def _check(self, rc):
+        cur, self._order_cur = self._order_cur, None
+        if cur is not None:                      # the caller's torch stream continues after the library's work
+            cur.wait_stream(self._lib_stream)
         if rc != 0:
             raise ZkbError(rc, self.lib.zkb_last_error(self.handle).decode())
+
+    def _order_before(self):
+        """A device buffer is about to be handed to the library: if the caller's current torch stream is not the library's
+        stream (marlin.Ops makes it so for the resident prover), the library stream first waits for what the caller has
+        enqueued, and _check makes the caller's stream wait for the library afterwards -- tensors produced or consumed
+        by torch around a call need no manual synchronisation."""
+        if self._order_cur is not None or torch is None:
+            return
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream == self._stream_ptr:
+            return
+        if self._lib_stream is None:
+            self._lib_stream = torch.cuda.ExternalStream(self._stream_ptr)
+        self._lib_stream.wait_stream(cur)
+        self._order_cur = cur
+
+    def _addr(self, a):
+        """host or device address: the library copies with cudaMemcpyDefault (unified addressing), so every buffer
+        argument of the vector / polynomial / MSM entry points may live on either side"""
+        if a is None:
+            return None
+        if is_dev(a):
+            self._order_before()
+            return ctypes.c_void_p(a.data_ptr())
+        return _ptr(a)
 
     def close(self):
         if self.handle:
@@ -191,7 +213,7 @@ class Context:
         out = np.zeros(point_words(srs.curve, srs.group), dtype=np.uint64)
         oinf = np.zeros(1, dtype=np.uint8)
         fn = self.lib.zkb_msm_mont if mont else self.lib.zkb_msm
-        self._check(fn(self.handle, srs.handle, base_offset, _addr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
+        self._check(fn(self.handle, srs.handle, base_offset, self._addr(scalars), scalars.shape[0], _ptr(out), _ptr(oinf)))
         return out, bool(oinf[0])
 
     def msm_batch(self, srs_list, scalars_list, base_offsets=None, mont=False):
@@ -206,6 +228,8 @@ class Context:
         w = point_words(srs_list[0].curve, srs_list[0].group)
         handles = (ctypes.c_void_p * k)(*[s.handle for s in srs_list])
         offs = (ctypes.c_size_t * k)(*base_offsets)
+        if any(is_dev(a) for a in sc):
+            self._order_before()
         ptrs = (ctypes.c_void_p * k)(*[(a.data_ptr() if is_dev(a) else a.ctypes.data) if a.shape[0] else None for a in sc])
         lens = (ctypes.c_size_t * k)(*[a.shape[0] for a in sc])
         out = np.zeros((k, w), dtype=np.uint64)
@@ -317,7 +341,7 @@ class Context:
         scalars = _fr(scalars)
         out = np.zeros(point_words(srs_shard.curve, srs_shard.group), dtype=np.uint64)
         oinf = np.zeros(1, dtype=np.uint8)
-        self._check(self.lib.zkb_msm_sharded(self.handle, srs_shard.handle, base_offset, _addr(scalars), scalars.shape[0],
+        self._check(self.lib.zkb_msm_sharded(self.handle, srs_shard.handle, base_offset, self._addr(scalars), scalars.shape[0],
                                              1 if mont else 0, _ptr(out), _ptr(oinf)))
         return out, bool(oinf[0])
 
@@ -333,7 +357,7 @@ class Context:
         """this rank's partial point as opaque bytes (for a caller-supplied transport)"""
         scalars = _fr(scalars)
         out = np.zeros(int(self.lib.zkb_partial_bytes(srs_shard.curve, srs_shard.group)), dtype=np.uint8)
-        self._check(self.lib.zkb_msm_partial(self.handle, srs_shard.handle, base_offset, _addr(scalars), scalars.shape[0],
+        self._check(self.lib.zkb_msm_partial(self.handle, srs_shard.handle, base_offset, self._addr(scalars), scalars.shape[0],
                                              1 if mont else 0, _ptr(out)))
         return out
 
@@ -384,6 +408,7 @@ class Context:
         if is_dev(data):
             if not (data.dtype == torch.int64 and data.is_contiguous() and tuple(data.shape) == (1 << log_n, 4)):
                 raise ValueError("data must be a contiguous CUDA int64[2^log_n, 4] tensor")
+            self._order_before()
             self._check(self.lib.zkb_ntt_dev(self.handle, curve, ctypes.c_void_p(data.data_ptr()), log_n, flags))
             return data
         if not (isinstance(data, np.ndarray) and data.dtype == np.uint64 and data.flags.c_contiguous
@@ -399,7 +424,7 @@ class Context:
     def fr_convert(self, curve, a, to_mont):
         a = _fr(a, "elements")
         out = _out_like(a, a.shape[0])
-        self._check(self.lib.zkb_fr_convert(self.handle, curve, _addr(a), _addr(out), a.shape[0], 1 if to_mont else 0))
+        self._check(self.lib.zkb_fr_convert(self.handle, curve, self._addr(a), self._addr(out), a.shape[0], 1 if to_mont else 0))
         return out
 
     # -- polynomial helpers (Marlin) ---------------------------------------------------------------
@@ -410,8 +435,8 @@ class Context:
         n = p.shape[0]
         q = _out_like(p, max(n - 1, 0)) if want_quotient else None
         rem = np.zeros(4, dtype=np.uint64)
-        self._check(self.lib.zkb_poly_div_linear(self.handle, curve, _addr(p), n, _ptr(z),
-                                                 _addr(q) if (want_quotient and n > 1) else None, _ptr(rem)))
+        self._check(self.lib.zkb_poly_div_linear(self.handle, curve, self._addr(p), n, _ptr(z),
+                                                 self._addr(q) if (want_quotient and n > 1) else None, _ptr(rem)))
         return q, rem
 
     def poly_eval(self, curve, p_mont, z_mont):
@@ -427,6 +452,8 @@ class Context:
         out = np.zeros((k, 4), dtype=np.uint64)
         if k == 0:
             return out
+        if any(is_dev(p) for p in polys):
+            self._order_before()
         ptrs = (ctypes.c_void_p * k)(*[(p.data_ptr() if is_dev(p) else p.ctypes.data) if len(p) else None for p in polys])
         lens = (ctypes.c_size_t * k)(*[len(p) for p in polys])
         self._check(self.lib.zkb_poly_eval_batch(self.handle, curve, k, ptrs, lens, _ptr(pts), _ptr(out)))
@@ -442,25 +469,27 @@ class Context:
         coeffs = _fr(coeffs_mont, "coefficients")
         if coeffs.shape[0] != k:
             raise ValueError("one coefficient per polynomial")
+        if any(is_dev(p) for p in polys):
+            self._order_before()
         ptrs = (ctypes.c_void_p * max(k, 1))(*[p.data_ptr() if is_dev(p) else p.ctypes.data for p in polys])
         lens = (ctypes.c_size_t * max(k, 1))(*[len(p) for p in polys])
         shs = (ctypes.c_size_t * max(k, 1))(*shifts)
         dev = [p for p in polys if is_dev(p)]
         out = _out_like(dev[0], out_len) if dev else np.zeros((out_len, 4), dtype=np.uint64)
-        self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), _addr(out), out_len))
+        self._check(self.lib.zkb_poly_lincomb(self.handle, curve, k, ptrs, lens, shs, _ptr(coeffs), self._addr(out), out_len))
         return out
 
     def fr_prefix_product(self, curve, a_mont):
         """out[i] = a[0] * ... * a[i - 1] (out[0] = 1)"""
         a = _fr(a_mont, "elements")
         out = _out_like(a, a.shape[0])
-        self._check(self.lib.zkb_fr_prefix_product(self.handle, curve, _addr(a), _addr(out), a.shape[0]))
+        self._check(self.lib.zkb_fr_prefix_product(self.handle, curve, self._addr(a), self._addr(out), a.shape[0]))
         return out
 
     def fr_batch_inverse(self, curve, a_mont):
         a = _fr(a_mont, "elements")
         out = _out_like(a, a.shape[0])
-        self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, _addr(a), _addr(out), a.shape[0]))
+        self._check(self.lib.zkb_fr_batch_inverse(self.handle, curve, self._addr(a), self._addr(out), a.shape[0]))
         return out
 
     VEC_ADD, VEC_SUB, VEC_MUL, VEC_SCALE, VEC_AXPY, VEC_RSUB, VEC_ADDC = range(7)
@@ -473,14 +502,14 @@ class Context:
             raise ValueError("operand shapes differ")
         s = None if s is None else np.ascontiguousarray(s, dtype=np.uint64).reshape(4)
         out = _out_like(a, a.shape[0])
-        self._check(self.lib.zkb_fr_vec_op(self.handle, curve, op, _addr(a), _addr(b), _ptr(s), _addr(out), a.shape[0]))
+        self._check(self.lib.zkb_fr_vec_op(self.handle, curve, op, self._addr(a), self._addr(b), _ptr(s), self._addr(out), a.shape[0]))
         return out
 
     def fr_powers(self, curve, base_mont, n, scale_mont=None, device=None):
         base = np.ascontiguousarray(base_mont, dtype=np.uint64).reshape(4)
         sc = None if scale_mont is None else np.ascontiguousarray(scale_mont, dtype=np.uint64).reshape(4)
         out = np.zeros((n, 4), dtype=np.uint64) if device is None else torch.empty((n, 4), dtype=torch.int64, device=device)
-        self._check(self.lib.zkb_fr_powers(self.handle, curve, _ptr(base), _ptr(sc), _addr(out), n))
+        self._check(self.lib.zkb_fr_powers(self.handle, curve, _ptr(base), _ptr(sc), self._addr(out), n))
         return out
 
     def spmv(self, curve, m, x_mont):
@@ -488,7 +517,7 @@ class Context:
         if m.max_col >= x.shape[0]:          # the kernel reads x[col] unchecked: a malformed matrix must not reach the device
             raise ValueError("CSR column index %d out of range for a vector of %d elements" % (m.max_col, x.shape[0]))
         y = _out_like(x, m.n_rows)
-        self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), _addr(x), x.shape[0], _addr(y)))
+        self._check(self.lib.zkb_spmv(self.handle, curve, ctypes.byref(m.c), self._addr(x), x.shape[0], self._addr(y)))
         return y
 
     # -- Groth16 ------------------------------------------------------------------------------
