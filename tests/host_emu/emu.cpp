@@ -75,7 +75,8 @@ template <class F, class FrP> static int decompress_one(const uint8_t* bytes, in
 }
 
 
-// pairing.cuh: stage 0 = Miller loop only, 1 = final exponentiation of `f_in`, 2 = both.  Points are affine Montgomery
+// pairing.cuh: stage 0 = affine Miller loop only, 1 = final exponentiation of `f_in`, 2 = projective loop + final
+// exponentiation (what the kernels run), 3 = affine loop + final exponentiation.  Points are affine Montgomery
 // limbs (G1: x,y; G2: x.c0,x.c1,y.c0,y.c1); f_in / out are 12 Fq in tower order, canonical (non-Montgomery) limbs.
 template <class PP> static void pairing_stage(int stage, const uint32_t* p, const uint32_t* q, const uint32_t* f_in, uint32_t* out) {
   using PT = PairingT<PP>;
@@ -91,7 +92,8 @@ template <class PP> static void pairing_stage(int stage, const uint32_t* p, cons
     memcpy(&xP, p, sizeof(xP)); memcpy(&yP, p + Fq::N, sizeof(yP));
     memcpy(&xQ, q, sizeof(xQ)); memcpy(&yQ, q + 2 * Fq::N, sizeof(yQ));
     bool pi = xP.is_zero() && yP.is_zero(), qi = xQ.is_zero() && yQ.is_zero();
-    PT::miller_loop(f, xP, yP, pi, xQ, yQ, qi);
+    if (stage == 0 || stage == 3) PT::miller_loop_affine(f, xP, yP, pi, xQ, yQ, qi);
+    else PT::miller_loop(f, xP, yP, pi, xQ, yQ, qi);        // stage 2: the inversion-free loop the kernels run
   }
   if (stage >= 1) { PT::final_exponentiation(r, f); f = r; }
   PT::f12_from_mont(f);

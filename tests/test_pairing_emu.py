@@ -1,6 +1,7 @@
 """csrc/pairing.cuh compiled for the host (tests/host_emu): the exact device code of the Miller loop and of the final
-exponentiation against the oracle's pairing (oracle/pyref/pairing.py), without a GPU.  The Miller-loop value is the
-oracle's bit for bit (same affine steps, same line scaling); the final exponentiation is the oracle's plain power
+exponentiation against the oracle's pairing (oracle/pyref/pairing.py), without a GPU.  The affine Miller-loop value is the
+oracle's bit for bit (same steps, same line scaling); the inversion-free loop the kernels run differs from it by a factor in
+Fq2* and must give the same pairing; the final exponentiation is the oracle's plain power
 f^((q^12 - 1) / r) raised to m = 3 on BLS12-381 (x-chain of the hard part) and m = 1 on BN254 (exact chain)."""
 import random
 
@@ -64,7 +65,8 @@ def test_miller_loop_and_final_exponentiation_match_oracle(lib, cid):
         assert tower_to_flat(cid, run(lib, cid, 0, P, Q)) == want
         fe = F12.pow(OP.final_exponentiation(cid, want), m)
         assert tower_to_flat(cid, run(lib, cid, 1, None, None, flat_to_tower(cid, want))) == fe
-        assert tower_to_flat(cid, run(lib, cid, 2, P, Q)) == fe
+        assert tower_to_flat(cid, run(lib, cid, 2, P, Q)) == fe          # the inversion-free loop of the kernels: same pairing
+        assert tower_to_flat(cid, run(lib, cid, 3, P, Q)) == fe          # affine loop + final exponentiation
     # identity on either side: the loop value is 1, and so is the pairing
     assert tower_to_flat(cid, run(lib, cid, 0, None, Q)) == F12.one
     assert tower_to_flat(cid, run(lib, cid, 2, P, None)) == F12.one
