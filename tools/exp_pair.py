@@ -22,6 +22,7 @@ ap.add_argument("--levels", type=int, nargs="*", default=[0, 1, 2, 3])
 ap.add_argument("--scales", type=int, nargs="*", default=[0, 1, 2, 4])
 ap.add_argument("--groups", type=int, nargs="*", default=[1, 2])
 ap.add_argument("--batch", type=int, nargs="*", default=[0], help="ZKB_MSM_BATCH values (batched-affine accumulation, msm_batch.cuh)")
+ap.add_argument("--curve", type=int, default=1, help="0 = BN254, 1 = BLS12-381")
 a = ap.parse_args()
 ctx = Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream)
@@ -29,13 +30,13 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 rng = np.random.default_rng(11)
 for group in a.groups:
     n = 1 << (a.log_n if group == 1 else a.log_n - 1)
-    gen = synth.generator_mont(1, group)
+    gen = synth.generator_mont(a.curve, group)
     xs, infs = [], []
     for i in range(0, n, 1 << 18):
-        xy, inf = ctx.fixed_base_mul(1, group, gen, synth.random_exponents(rng, min(1 << 18, n - i)))
+        xy, inf = ctx.fixed_base_mul(a.curve, group, gen, synth.random_exponents(rng, min(1 << 18, n - i)))
         xs.append(xy); infs.append(inf)
-    srs = ctx.srs_upload(1, group, np.concatenate(xs), np.concatenate(infs))
-    d = torch.from_numpy(synth.random_scalars(rng, n, 1).view(np.int64)).cuda()
+    srs = ctx.srs_upload(a.curve, group, np.concatenate(xs), np.concatenate(infs))
+    d = torch.from_numpy(synth.random_scalars(rng, n, a.curve).view(np.int64)).cuda()
     base = None
     for lv, bt in [(lv, bt) for bt in a.batch for lv in a.levels]:
         for sc in (a.scales if lv else [0]):
