@@ -3,11 +3,11 @@
 // Replaces what groth16/src/verifier.rs:18-44 (`verify_proof`: three Miller loops, one final exponentiation) and
 // marlin/src/pc/kzg10.rs `check` / `batch_check` obtain from ark-ec 0.2's `PairingEngine` (un-vendored).  Those callers
 // only compare GT elements, so any non-degenerate bilinear pairing on (G1, G2) gives the same accept / reject decision;
-// this file computes the plain ate pairing
+// this file computes
 //
-//     a(Q, P) = f_{|t - 1|, Q}(P) ^ (m (q^12 - 1) / r),      |t - 1| = |x| (BLS12-381), 6 x^2 (BN254),
-//
-// with m = 3 on BLS12-381 (the x-chain of the hard part yields the cube; gcd(3, r) = 1) and m = 1 on BN254.
+//     BLS12-381:  f_{|x|, Q}(P) ^ (3 (q^12 - 1) / r)        (plain ate, loop |t - 1| = |x|; the x-chain of the hard part
+//                                                            yields the cube, gcd(3, r) = 1)
+//     BN254:      (f_{6x+2, Q}(P) l_{[6x+2]Q, pi(Q)}(P) l_{[6x+2]Q + pi(Q), -pi^2(Q)}(P)) ^ ((q^12 - 1) / r)    (optimal ate)
 //
 // Work distribution: a verifier checks MANY proofs, so the unit of parallelism is the pair -- one thread runs one Miller
 // loop (homogeneous doubling / addition steps on the twist, sparse products by the lines; the affine form with one Fq2
@@ -163,7 +163,26 @@ struct PairingT {
     }
   }
 
-  // f_{|t-1|, Q}(P); P in G1 (affine over Fq), Q in G2 (affine on the twist over Fq2); identity on either side -> 1.
+  // pi_q on the twist (psi^-1 o Frobenius o psi): (x', y') -> (conj(x') gamma_2, conj(y') gamma_3)
+  ZKB_HD static void frob_twist(F2& xo, F2& yo, const F2& x, const F2& y) {
+    xo = F2::mul(conj(x), frob_const(2));
+    yo = F2::mul(conj(y), frob_const(3));
+  }
+  // f <- f * l_{T,R}(P), T <- T + R  (R affine on the twist)
+  ZKB_HD static void add_step_affine(F12& f, F2& tx, F2& ty, const F2& xR, const F2& yR, const FC& xP, const FC& yP) {
+    F12 l, t;
+    F2 lam = F2::mul(F2::sub(yR, ty), F2::inv_fast(F2::sub(xR, tx)));
+    line(l, lam, tx, ty, xP, yP);
+    f12_mul(t, f, l);
+    f = t;
+    F2 x3 = F2::sub(F2::sub(F2::sqr(lam), tx), xR);
+    ty = F2::sub(F2::mul(lam, F2::sub(tx, x3)), ty);
+    tx = x3;
+  }
+
+  // The Miller function: f_{|x|, Q}(P) on BLS12-381 (plain ate); on BN254 the optimal ate
+  // f_{6x+2, Q}(P) l_{[6x+2]Q, pi(Q)}(P) l_{[6x+2]Q + pi(Q), -pi^2(Q)}(P).
+  // P in G1 (affine over Fq), Q in G2 (affine on the twist over Fq2); identity on either side -> 1.
   // Q must lie in the order-r subgroup (no vertical line can then occur before the loop ends).
   static ZKB_NOINLINE void miller_loop_affine(F12& f, const FC& xP, const FC& yP, bool p_inf, const F2& xQ, const F2& yQ, bool q_inf) {
     f = f12_one();
@@ -179,15 +198,14 @@ struct PairingT {
       F2 x3 = F2::sub(F2::sqr(lam), F2::dbl(tx));
       ty = F2::sub(F2::mul(lam, F2::sub(tx, x3)), ty);
       tx = x3;
-      if ((PP::loop(i >> 5) >> (i & 31)) & 1) {
-        lam = F2::mul(F2::sub(yQ, ty), F2::inv_fast(F2::sub(xQ, tx)));
-        line(l, lam, tx, ty, xP, yP);
-        f12_mul(t, f, l);
-        f = t;
-        x3 = F2::sub(F2::sub(F2::sqr(lam), tx), xQ);
-        ty = F2::sub(F2::mul(lam, F2::sub(tx, x3)), ty);
-        tx = x3;
-      }
+      if ((PP::loop(i >> 5) >> (i & 31)) & 1) add_step_affine(f, tx, ty, xQ, yQ, xP, yP);
+    }
+    if (PP::OPT_ATE_BN) {                    // lines through pi(Q) and -pi^2(Q)
+      F2 x1, y1, x2, y2;
+      frob_twist(x1, y1, xQ, yQ);
+      frob_twist(x2, y2, x1, y1);
+      add_step_affine(f, tx, ty, x1, y1, xP, yP);
+      add_step_affine(f, tx, ty, x2, F2::neg(y2), xP, yP);
     }
   }
 
@@ -231,6 +249,22 @@ struct PairingT {
     if (!PP::TWIST_D) l0 = mul_xi(l0);
     lw = F2::neg(mul_fq(kx, xP));            // -(scale * slope) xP
   }
+  static ZKB_NOINLINE void add_step(F12& f, F2& X, F2& Y, F2& Z, const F2& xR, const F2& yR, const FC& xP, const FC& yP) {
+    F12 t;
+    F2 l0, lw, l3;
+    F2 u = F2::sub(F2::mul(yR, Z), Y), v = F2::sub(F2::mul(xR, Z), X);
+    line_coeffs(l0, lw, v, u, xP, yP);
+    l3 = F2::sub(F2::mul(u, xR), F2::mul(v, yR));
+    F2 vv = F2::sqr(v);
+    F2 vvv = F2::mul(v, vv);
+    F2 R = F2::mul(vv, X);
+    F2 A = F2::sub(F2::sub(F2::mul(F2::sqr(u), Z), vvv), F2::dbl(R));
+    X = F2::mul(v, A);
+    Y = F2::sub(F2::mul(u, F2::sub(R, A)), F2::mul(vvv, Y));
+    Z = F2::mul(vvv, Z);
+    f12_mul_by_line(t, f, l0, lw, l3);
+    f = t;
+  }
   static ZKB_NOINLINE void miller_loop(F12& f, const FC& xP, const FC& yP, bool p_inf, const F2& xQ, const F2& yQ, bool q_inf) {
     f = f12_one();
     if (p_inf || q_inf) return;
@@ -254,20 +288,14 @@ struct PairingT {
       }
       f12_sqr(t, f);
       f12_mul_by_line(f, t, l0, lw, l3);
-      if ((PP::loop(i >> 5) >> (i & 31)) & 1) {
-        F2 u = F2::sub(F2::mul(yQ, Z), Y), v = F2::sub(F2::mul(xQ, Z), X);
-        line_coeffs(l0, lw, v, u, xP, yP);
-        l3 = F2::sub(F2::mul(u, xQ), F2::mul(v, yQ));
-        F2 vv = F2::sqr(v);
-        F2 vvv = F2::mul(v, vv);
-        F2 R = F2::mul(vv, X);
-        F2 A = F2::sub(F2::sub(F2::mul(F2::sqr(u), Z), vvv), F2::dbl(R));
-        X = F2::mul(v, A);
-        Y = F2::sub(F2::mul(u, F2::sub(R, A)), F2::mul(vvv, Y));
-        Z = F2::mul(vvv, Z);
-        f12_mul_by_line(t, f, l0, lw, l3);
-        f = t;
-      }
+      if ((PP::loop(i >> 5) >> (i & 31)) & 1) add_step(f, X, Y, Z, xQ, yQ, xP, yP);
+    }
+    if (PP::OPT_ATE_BN) {
+      F2 x1, y1, x2, y2;
+      frob_twist(x1, y1, xQ, yQ);
+      frob_twist(x2, y2, x1, y1);
+      add_step(f, X, Y, Z, x1, y1, xP, yP);
+      add_step(f, X, Y, Z, x2, F2::neg(y2), xP, yP);
     }
   }
 

@@ -252,8 +252,9 @@ int zkb_points_decompress(zkb_ctx* ctx, int curve, int group, const uint8_t* com
  * with alpha_g1_beta_g2) and marlin/src/pc/kzg10.rs `check` / `batch_check` obtain from ark-ec's PairingEngine, for many
  * proofs at once.  Pairs are laid out group after group: group g is pairs [g * group_size, (g + 1) * group_size) and
  *     out_gt[g] = prod_j a(P_j, Q_j)
- * with a = the reduced ate pairing f_{|t-1|,Q}(P)^(m (q^12 - 1) / r), m = 3 on BLS12-381 and 1 on BN254 (a fixed power
- * of the pairing ark-ec computes: equalities between products -- all these callers test -- hold or fail identically).
+ * with a = a reduced pairing chosen for the device: the plain ate f_{|x|,Q}(P)^(3 (q^12 - 1) / r) on BLS12-381, the optimal
+ * ate on BN254 (a fixed power of the pairing ark-ec computes: equalities between products -- all these callers test --
+ * hold or fail identically).
  * g1_xy / g2_xy: affine Montgomery points as everywhere in this ABI, *_inf optional identity flags (an all-zero point
  * is the identity too; a pair with an identity contributes 1).  G2 points must be in the order-r subgroup.
  * out_gt: n_groups x 12 x limbs(Fq) Montgomery limbs in the tower order of ark-ff's Fq12 (c0.c0.c0, c0.c0.c1, c0.c1.c0,

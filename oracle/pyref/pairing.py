@@ -116,6 +116,74 @@ def miller_loop(cid, P, Q):
     return f
 
 
+def _frobenius_twist(cid, Q):
+    """pi_q on a point of the (D-type) twist: psi^-1 o Frobenius o psi, (x', y') -> (conj(x') xi^((q-1)/3), conj(y') xi^((q-1)/2))"""
+    F2 = CURVES[(cid, 2)].F
+    q, c = FQ[cid].p, _C[cid]
+
+    def f2_pow(a, e):
+        r = (1, 0)
+        while e:
+            if e & 1:
+                r = F2.mul(r, a)
+            a = F2.sqr(a)
+            e >>= 1
+        return r
+
+    conj = lambda z: (z[0], (-z[1]) % q)
+    g2, g3 = f2_pow((c, 1), (q - 1) // 3), f2_pow((c, 1), (q - 1) // 2)
+    return (F2.mul(conj(Q[0]), g2), F2.mul(conj(Q[1]), g3))
+
+
+def miller_loop_optimal_bn(cid, P, Q):
+    """The optimal ate Miller function of a BN curve (Vercauteren): f_{6x+2,Q}(P) * l_{[6x+2]Q, pi(Q)}(P) *
+    l_{[6x+2]Q + pi(Q), -pi^2(Q)}(P), x > 0 -- half the loop length of miller_loop.  Same affine steps and line scaling
+    as miller_loop; this is what csrc/pairing.cuh runs on BN254 (a different power of the same pairing)."""
+    assert cid == BN254 and _X[cid] > 0
+    F12 = Fq12(cid)
+    if P is None or Q is None:
+        return F12.one
+    g2 = CURVES[(cid, 2)]
+    F2 = g2.F
+    n = 6 * _X[cid] + 2
+    f, T = F12.one, Q
+    three = F2.small(3)
+
+    def add_step(f, T, R):
+        lam = F2.mul(F2.sub(R[1], T[1]), F2.inv(F2.sub(R[0], T[0])))
+        f = F12.mul(f, _line(F12, F2, cid, T, lam, P))
+        x3 = F2.sub(F2.sub(F2.sqr(lam), T[0]), R[0])
+        return f, (x3, F2.sub(F2.mul(lam, F2.sub(T[0], x3)), T[1]))
+
+    for i in reversed(range(n.bit_length() - 1)):
+        lam = F2.mul(F2.mul(three, F2.sqr(T[0])), F2.inv(F2.add(T[1], T[1])))
+        f = F12.mul(F12.sqr(f), _line(F12, F2, cid, T, lam, P))
+        x3 = F2.sub(F2.sqr(lam), F2.add(T[0], T[0]))
+        T = (x3, F2.sub(F2.mul(lam, F2.sub(T[0], x3)), T[1]))
+        if (n >> i) & 1:
+            f, T = add_step(f, T, Q)
+    Q1 = _frobenius_twist(cid, Q)
+    Q2 = g2.neg_affine(_frobenius_twist(cid, Q1))
+    f, T = add_step(f, T, Q1)
+    f, T = add_step(f, T, Q2)
+    return f
+
+
+def device_miller_loop(cid, P, Q):
+    """the Miller function csrc/pairing.cuh computes: optimal ate on BN254, plain ate (loop |x|) on BLS12-381"""
+    return miller_loop_optimal_bn(cid, P, Q) if cid == BN254 else miller_loop(cid, P, Q)
+
+
+def device_multi_pairing(cid, pairs):
+    """what zkb_multi_pairing returns for one group: the product of the device's Miller functions to the power
+    m (q^12 - 1) / r, m = 3 on BLS12-381 (x-chain of the hard part), 1 on BN254"""
+    F12 = Fq12(cid)
+    f = F12.one
+    for P, Q in pairs:
+        f = F12.mul(f, device_miller_loop(cid, P, Q))
+    return F12.pow(final_exponentiation(cid, f), 3 if cid == BLS12_381 else 1)
+
+
 def final_exponentiation(cid, f):
     q, r = FQ[cid].p, FR[cid].p
     return Fq12(cid).pow(f, (q ** 12 - 1) // r)

@@ -90,3 +90,25 @@ def test_golden_mimc_proof_is_accepted():
     proof = tuple(H.array_point(cid, grp, g[k + "_xy"][0], bool(g[k + "_inf"][0]))
                   for k, grp in (("proof_a", 1), ("proof_b", 2), ("proof_c", 1)))
     assert OG.verify_proof(pk, proof, cs.input_assignment[1:])
+
+
+def test_optimal_ate_on_bn254_is_a_pairing():
+    """miller_loop_optimal_bn (what csrc/pairing.cuh runs on BN254): the Frobenius of a twist point is [q]Q on G2, the
+    result is bilinear and non-degenerate, and it decides pairing-product equalities like the plain ate pairing"""
+    from oracle.pyref import pairing as OP
+    from oracle.pyref.curves import CURVES
+    from oracle.pyref.fields import FQ
+    cid = BN254
+    g1, g2 = CURVES[(cid, 1)], CURVES[(cid, 2)]
+    Q = g2.mul_affine(g2.gen, 987654321)
+    assert OP._frobenius_twist(cid, Q) == g2.mul_affine(Q, FQ[cid].p % g2.r)
+    a, b = 0x1F2E3D4C5B6A, 0x123456789ABCDEF
+    one = OP.Fq12(cid).one
+    e_ab = OP.device_multi_pairing(cid, [(g1.mul_affine(g1.gen, a), g2.mul_affine(g2.gen, b))])
+    assert e_ab == OP.device_multi_pairing(cid, [(g1.mul_affine(g1.gen, a * b % g1.r), g2.gen)]) != one
+    assert e_ab == OP.device_multi_pairing(cid, [(g1.gen, g2.mul_affine(g2.gen, a * b % g1.r))])
+    # e(aP, Q) e(-P, aQ) == 1 under both pairings; e(aP, Q) e(-P, (a + 1) Q) != 1 under both
+    good = [(g1.mul_affine(g1.gen, a), Q), (g1.neg_affine(g1.gen), g2.mul_affine(Q, a))]
+    bad = [(g1.mul_affine(g1.gen, a), Q), (g1.neg_affine(g1.gen), g2.mul_affine(Q, a + 1))]
+    assert OP.device_multi_pairing(cid, good) == one and OP.multi_pairing(cid, good) == one
+    assert OP.device_multi_pairing(cid, bad) != one and OP.multi_pairing(cid, bad) != one
