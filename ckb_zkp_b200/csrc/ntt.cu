@@ -88,7 +88,6 @@ k_ntt_pass(const Fp<FrP>* src, Fp<FrP>* dst, const Fp<FrP>* __restrict__ tw, uns
   // Two stages per shared-memory round trip (radix-4 step: four elements in registers, three twiddles, four
   // multiplications, one barrier) while at least two stages remain; an odd stage count ends with one radix-2 stage.
   unsigned q = 0;
-  const bool skip_unit = (radix4 & 2) == 0;
   if (radix4) {
     for (; q + 1 < k; q += 2) {
       for (unsigned i = threadIdx.x; i < E / 4; i += blockDim.x) {
@@ -104,15 +103,10 @@ k_ntt_pass(const Fp<FrP>* src, Fp<FrP>* dst, const Fp<FrP>* __restrict__ tw, uns
         Fr a0, a1, a2, a3;
 #pragma unroll
         for (int x = 0; x < Fr::N; x++) { a0.v[x] = sm[x * E + e0]; a1.v[x] = sm[x * E + e1]; a2.v[x] = sm[x * E + e2]; a3.v[x] = sm[x * E + e3]; }
-        // the very first step of a transform (s0 + q == 0) has w1 = w2a = 1: three of its four products are skipped
-        // (uniform over the grid, no divergence) -- 1.5 of the log_n stages' multiplications
-        const bool unit = (s0 + q) == 0 && skip_unit;
-        if (!unit) {
-          a1 = Fr::mul(a1, w1);
-          a3 = Fr::mul(a3, w1);
-        }
+        a1 = Fr::mul(a1, w1);
+        a3 = Fr::mul(a3, w1);
         Fr b0 = Fr::add(a0, a1), b1 = Fr::sub(a0, a1), b2 = Fr::add(a2, a3), b3 = Fr::sub(a2, a3);
-        if (!unit) b2 = Fr::mul(b2, w2a);
+        b2 = Fr::mul(b2, w2a);
         b3 = Fr::mul(b3, w2b);
         a0 = Fr::add(b0, b2); a2 = Fr::sub(b0, b2); a1 = Fr::add(b1, b3); a3 = Fr::sub(b1, b3);
 #pragma unroll
