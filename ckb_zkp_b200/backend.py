@@ -146,11 +146,12 @@ class Context:
         by torch around a call need no manual synchronisation."""
         if self._order_cur is not None or torch is None:
             return
-        cur = torch.cuda.current_stream()
+        dev = torch.device("cuda", self.device)          # the context's device, whatever torch's current device is
+        cur = torch.cuda.current_stream(dev)
         if cur.cuda_stream == self._stream_ptr:
             return
         if self._lib_stream is None:
-            self._lib_stream = torch.cuda.ExternalStream(self._stream_ptr)
+            self._lib_stream = torch.cuda.ExternalStream(self._stream_ptr, device=dev)
         self._lib_stream.wait_stream(cur)
         self._order_cur = cur
 
