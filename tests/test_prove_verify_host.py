@@ -81,3 +81,29 @@ def test_plonk_keygen_prove_verify_over_mock(cid):
     assert not zp.verify(ctx, vk, pis, swapped)
     tampered = zp.Proof(proof.commitments, [(proof.evaluations[0] + 1) % p] + proof.evaluations[1:], proof.openings)
     assert not zp.verify(ctx, vk, pis, tampered)
+
+
+@pytest.mark.parametrize("cid", [BN254, BLS12_381])
+def test_groth16_generator_over_mock(cid):
+    """generate_parameters (groth16/src/generator.rs:135-286) host logic on the CPU against the oracle's generator on the
+    same toxic waste: every query and the verifying key"""
+    import numpy as np
+    from ckb_zkp_b200 import generator as zgen
+    from oracle.pyref import groth16 as OG
+    from oracle.pyref.fields import stream_field
+    from oracle.pyref.r1cs import ConstraintSystem, mini_circuit
+    from tests.test_gpu_generator import MiniCircuit, same_points
+    ctx = MockProverVerifierContext()
+    p = FR[cid].p
+    alpha, beta, gamma, delta, t = [stream_field(7, i, p) for i in range(5)]
+    want = OG.generate_parameters(mini_circuit(ConstraintSystem(p)), cid, alpha, beta, gamma, delta, t)
+    got = zgen.generate_parameters(ctx, cid, MiniCircuit(2, 3, 10, 10), alpha, beta, gamma, delta, t)
+    same_points(cid, 1, got.a_query, want.a_query)
+    same_points(cid, 1, got.b_g1_query, want.b_g1_query)
+    same_points(cid, 2, got.b_g2_query, want.b_g2_query)
+    same_points(cid, 1, got.h_query, want.h_query)
+    same_points(cid, 1, got.l_query, want.l_query)
+    same_points(cid, 1, got.vk.gamma_abc_g1, want.gamma_abc_g1)
+    one = lambda pt: ([pt[0]], [1 if pt[1] else 0])
+    same_points(cid, 1, one(got.vk.alpha_g1), [want.alpha_g1])
+    same_points(cid, 2, one(got.vk.delta_g2), [want.delta_g2])
