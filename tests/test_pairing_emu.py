@@ -82,3 +82,13 @@ def test_bilinear(lib, cid):
     e1 = run(lib, cid, 2, g1.mul_affine(g1.gen, a), g2.mul_affine(g2.gen, b))
     e2 = run(lib, cid, 2, g1.mul_affine(g1.gen, a * b % g1.r), g2.gen)
     assert e1 == e2 and e1 != flat_to_tower(cid, OP.Fq12(cid).one)
+
+
+def test_pairing_params_header_is_generated():
+    """csrc/pairing_params.cuh (loop counts, Frobenius constants) is what tools/gen_pairing_params.py derives from the moduli"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.call([sys.executable, os.path.join(root, "tools", "gen_pairing_params.py"), "--check"]) == 0
+
